@@ -1,0 +1,173 @@
+"""CPU oracle for the VisualBERT encoder hot path — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+A plain functional restatement (torch tensor algebra, any float dtype, CPU or GPU) of the
+reference algorithm in uclanlp/visualbert `visualbert/pytorch_pretrained_bert/modeling.py`
+("M.py" below). Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference arm may
+import this module, and only as the checker. The product path (visualbert_b200) never imports it.
+
+Parity pinning: the reference repo holds NO tests, golden vectors or known-answer fixtures for this
+path, so the oracle is pinned against outputs of the reference itself, generated
+in the build container by oracle/make_golden.py (which imports the unmodified reference from
+/root/reference) and committed under tests/golden/. tests/test_oracle_golden.py checks this module
+against those fixtures on every CPU test run.
+
+State is a dict name -> tensor using the reference's state_dict keys, e.g.
+`bert.encoder.layer.0.attention.self.query.weight`.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+def gelu(x):
+    """M.py:56-61 — exact erf form."""
+    return x * 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0)))
+
+
+def layer_norm(x, weight, bias, eps=1e-12):
+    """M.py:171-175 — TF style: biased variance, eps inside the sqrt."""
+    u = x.mean(-1, keepdim=True)
+    s = (x - u).pow(2).mean(-1, keepdim=True)
+    return weight * ((x - u) / torch.sqrt(s + eps)) + bias
+
+
+def linear(x, sd, prefix):
+    return F.linear(x, sd[prefix + ".weight"], sd[prefix + ".bias"])
+
+
+def embeddings(sd, input_ids, token_type_ids, visual_embeddings, visual_embeddings_type,
+               image_text_alignment=None, pfx="bert.embeddings."):
+    """M.py:1198-1257 (dropout omitted: eval mode). Text first, then visual; every region uses
+    visual position row 0 (M.py:1247); optional VCR alignment branch M.py:1223-1245."""
+    T = input_ids.size(1)
+    dt = sd[pfx + "word_embeddings.weight"].dtype
+    pos = torch.arange(T, device=input_ids.device)
+    e = (sd[pfx + "word_embeddings.weight"][input_ids]
+         + sd[pfx + "position_embeddings.weight"][pos].unsqueeze(0)
+         + sd[pfx + "token_type_embeddings.weight"][token_type_ids])
+    if visual_embeddings is not None:
+        v = F.linear(visual_embeddings.to(dt), sd[pfx + "projection.weight"], sd[pfx + "projection.bias"])
+        tv = sd[pfx + "token_type_embeddings_visual.weight"][visual_embeddings_type]
+        pv = sd[pfx + "position_embeddings_visual.weight"][0].view(1, 1, -1).expand_as(v)
+        if image_text_alignment is not None:
+            m = (image_text_alignment != -1).long()
+            ali = m * image_text_alignment
+            pa = sd[pfx + "position_embeddings.weight"][ali] * m.to(dt).unsqueeze(-1)
+            pa = pa.sum(2)
+            cnt = m.to(dt).sum(2)
+            cnt[cnt == 0] = 1
+            pa = pa / cnt.unsqueeze(-1)
+            pa = pa[:, : v.size(1), :]
+            pv = pa + pv
+        e = torch.cat((e, v + pv + tv), dim=1)
+    return layer_norm(e, sd[pfx + "LayerNorm.weight"], sd[pfx + "LayerNorm.bias"])
+
+
+def self_attention(sd, pfx, x, ext_mask, num_heads, return_probs=False):
+    """M.py:231-261: scale-then-mask, softmax, P·V, head merge."""
+    B, S, H = x.shape
+    d = H // num_heads
+
+    def split(t):
+        return t.view(B, S, num_heads, d).permute(0, 2, 1, 3)
+
+    q = split(linear(x, sd, pfx + "query"))
+    k = split(linear(x, sd, pfx + "key"))
+    v = split(linear(x, sd, pfx + "value"))
+    scores = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(d)
+    scores = scores + ext_mask
+    probs = torch.softmax(scores, dim=-1)
+    ctx = torch.matmul(probs, v).permute(0, 2, 1, 3).contiguous().view(B, S, H)
+    return (ctx, probs) if return_probs else ctx
+
+
+def bert_layer(sd, pfx, x, ext_mask, num_heads):
+    """M.py:331-341 with 270-274, 302-305, 315-319."""
+    ctx = self_attention(sd, pfx + "attention.self.", x, ext_mask, num_heads)
+    a = layer_norm(linear(ctx, sd, pfx + "attention.output.dense") + x,
+                   sd[pfx + "attention.output.LayerNorm.weight"], sd[pfx + "attention.output.LayerNorm.bias"])
+    h = gelu(linear(a, sd, pfx + "intermediate.dense"))
+    return layer_norm(linear(h, sd, pfx + "output.dense") + a,
+                      sd[pfx + "output.LayerNorm.weight"], sd[pfx + "output.LayerNorm.bias"])
+
+
+def visual_model(sd, cfg, input_ids, token_type_ids, attention_mask, visual_embeddings,
+                 visual_embeddings_type, image_text_alignment=None, pfx="bert."):
+    """BertVisualModel.forward, M.py:1275-1333 (default branch). Returns (all layers, pooled)."""
+    dt = sd[pfx + "embeddings.word_embeddings.weight"].dtype
+    ext = (1.0 - attention_mask[:, None, None, :].to(dt)) * -10000.0
+    x = embeddings(sd, input_ids, token_type_ids, visual_embeddings, visual_embeddings_type,
+                   image_text_alignment, pfx + "embeddings.")
+    layers = []
+    for i in range(cfg["num_hidden_layers"]):
+        x = bert_layer(sd, f"{pfx}encoder.layer.{i}.", x, ext, cfg["num_attention_heads"])
+        layers.append(x)
+    pooled = torch.tanh(linear(x[:, 0], sd, pfx + "pooler.dense"))  # M.py:380-386
+    return layers, pooled
+
+
+def _flat2(t):
+    return None if t is None else (t if t.dim() == 2 else t.contiguous().view(-1, t.size(-1)))
+
+
+def _flat3(t):
+    return None if t is None else (t if t.dim() == 3 else t.contiguous().view(-1, t.size(-2), t.size(-1)))
+
+
+def pretraining_heads(sd, seq, pooled):
+    """BertPreTrainingHeads, M.py:389-452; decoder weight tied to the word embeddings (M.py:414)."""
+    t = gelu(linear(seq, sd, "cls.predictions.transform.dense"))
+    t = layer_norm(t, sd["cls.predictions.transform.LayerNorm.weight"], sd["cls.predictions.transform.LayerNorm.bias"])
+    logits = F.linear(t, sd["bert.embeddings.word_embeddings.weight"]) + sd["cls.predictions.bias"]
+    return logits, linear(pooled, sd, "cls.seq_relationship")
+
+
+def objective(sd, cfg, head, input_ids, token_type_ids, input_mask, visual_embeddings, image_mask,
+              visual_embeddings_type=None, label=None, masked_lm_labels=None, is_random_next=None,
+              image_text_alignment=None):
+    """TrainVisualBERTObjective.forward, M.py:1373-1598 for heads pretraining / vqa / nlvr /
+    multichoice, eval mode (dropout off). Returns the reference's output dict."""
+    ids, tt, im = _flat2(input_ids), _flat2(token_type_ids), _flat2(input_mask)
+    vm, lab = _flat2(image_mask), _flat2(masked_lm_labels)
+    ve, ali = _flat3(visual_embeddings), _flat3(image_text_alignment)
+    vt = _flat2(visual_embeddings_type) if visual_embeddings_type is not None else torch.zeros_like(vm)
+    am = torch.cat((im, vm), dim=-1)
+    if lab is not None:
+        full = torch.full_like(am, -1)
+        full[:, : lab.size(1)] = lab
+        lab = full
+    layers, pooled = visual_model(sd, cfg, ids, tt, am, ve, vt, ali)
+    seq = layers[-1]
+    out = {"sequence_output": seq, "pooled_output": pooled}
+    if head == "pretraining":
+        logits, nsp = pretraining_heads(sd, seq, pooled)
+        out["logits"], out["seq_relationship_score"], out["loss"] = logits, nsp, None
+        if lab is not None:
+            mlm = F.cross_entropy(logits.view(-1, logits.size(-1)), lab.view(-1), ignore_index=-1)
+            out["masked_lm_loss"] = mlm
+            out["loss"] = mlm
+            if is_random_next is not None:
+                nl = F.cross_entropy(nsp.view(-1, 2), is_random_next.view(-1), ignore_index=-1)
+                out["next_sentence_loss"] = nl
+                out["loss"] = mlm + nl
+    elif head == "vqa":
+        idx = im.sum(1) - 2  # M.py:1504
+        g = seq[torch.arange(seq.size(0)), idx]
+        logits = linear(g, sd, "classifier")
+        out["logits"], out["loss"] = logits.unsqueeze(1), None
+        if label is not None:
+            out["loss"] = F.kl_div(torch.log_softmax(logits, -1), label, reduction="batchmean")
+    elif head == "nlvr":
+        logits = linear(pooled, sd, "classifier")
+        out["logits"], out["loss"] = logits, None
+        if label is not None:
+            out["loss"] = F.cross_entropy(logits, label)
+    elif head == "multichoice":
+        logits = linear(pooled, sd, "classifier").view(-1, 4)
+        out["logits"], out["loss"] = logits, None
+        if label is not None:
+            out["loss"] = F.cross_entropy(logits, label)
+    else:
+        raise ValueError(head)
+    return out

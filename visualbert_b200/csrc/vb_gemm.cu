@@ -1,0 +1,471 @@
+// vb_gemm.cu — the dense-contraction core of the VisualBERT encoder hot path on sm_100a.
+//
+// One persistent, warp-specialised kernel computes D[M,N] = epi(sum_k A(m,k) B(n,k)) in bf16 with
+// fp32 accumulation:
+//   warp 0     TMA producer  (cp.async.bulk.tensor, 128B-swizzled 64-wide tiles, 4-stage mbarrier ring)
+//   warp 1     MMA issuer    (one elected thread issues tcgen05.mma 128xBNx16, accumulators in TMEM,
+//                             two accumulator stages so the epilogue of tile i overlaps tile i+1)
+//   warp 2     TMEM allocator
+//   warps 4-11 epilogue      (tcgen05.ld -> bias / dropout / residual / GELU / GELU' -> 16-byte stores,
+//                             or fp32 red.add for split-K weight gradients)
+//
+// Replaces every nn.Linear on the path (reference modeling.py:232-234 Q/K/V, 271 attention output,
+// 303 intermediate, 316 output, 1220 visual projection) together with the element-wise work that
+// follows each of them (bias, dropout 272/317, residual add 273/318, gelu 304), and their autograd
+// backward (input gradients use B "MN-major", weight gradients use A and B "MN-major").
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "../../include/vbert_b200.h"
+#include "vb_common.cuh"
+
+namespace vb {
+
+// ---------------------------------------------------------------------------------------------
+// error + launch accounting (host)
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+// ---------------------------------------------------------------------------------------------
+// tile configuration
+// ---------------------------------------------------------------------------------------------
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle atom row
+constexpr int UMMA_K = 16;
+constexpr int kStages = 4;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 128 + kEpiWarps * 32;  // 384
+constexpr int kAtomBytes = 64 * BLOCK_K * 2;    // one 64(MN) x 64(K) bf16 swizzle atom = 8 KB
+
+template <int BLOCK_N>
+struct Cfg {
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+    static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFF = kStages * STAGE_BYTES;
+    static constexpr int NUM_BARS = 2 * kStages + 4;
+    static constexpr int TMEM_PTR_OFF = BAR_OFF + NUM_BARS * 8;
+    static constexpr int SMEM_BYTES = TMEM_PTR_OFF + 16 + 1024;  // +1024: manual 1 KB alignment
+    static constexpr int TMEM_COLS = 2 * BLOCK_N;                // power of two: 256 or 512
+};
+
+struct GemmParams {
+    int M, N, K;
+    int splits;
+    void* D; long long ldd;
+    const float* bias;
+    const bf16* addend; long long ld_add;
+    int epilogue;
+    const bf16* aux_in;
+    bf16* aux_out; long long ld_aux;
+    float drop_scale;        // 1/(1-p), 0 => dropout off
+    unsigned drop_thresh16;  // round(p * 65536)
+    unsigned long long drop_seed;
+    unsigned drop_stream;
+};
+
+// UMMA shared-memory matrix descriptor (sm_100: version = 1), SWIZZLE_128B.
+//  K-major  operand tile [rows][64]: 8-row groups are 1024 B apart (SBO); LBO unused.
+//  MN-major operand tile [atoms of 64 along MN][64 k-rows][64]: 8 k-rows = 1024 B (SBO),
+//           next 64-wide MN atom = 64 k-rows * 128 B = 8192 B (LBO).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;  // descriptor version (sm_100)
+    d |= 2ull << 61;  // SWIZZLE_128B
+    return d;
+}
+
+// tcgen05 instruction descriptor, kind::f16: D=f32, A=B=bf16, M=128, N=BLOCK_N, majors as given.
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn) << 15) |
+           (static_cast<uint32_t>(b_mn) << 16) | (static_cast<uint32_t>(n >> 3) << 17) |
+           (static_cast<uint32_t>(BLOCK_M >> 4) << 24);
+}
+
+struct TileCoord {
+    int m_blk, n_blk, kb_begin, kb_end;
+};
+__device__ __forceinline__ TileCoord decode_tile(int t, int n_blocks, int splits, int k_blocks) {
+    TileCoord c;
+    const int split = t % splits;
+    const int mn = t / splits;
+    c.n_blk = mn % n_blocks;
+    c.m_blk = mn / n_blocks;
+    c.kb_begin = static_cast<int>(static_cast<long long>(split) * k_blocks / splits);
+    c.kb_end = static_cast<int>(static_cast<long long>(split + 1) * k_blocks / splits);
+    return c;
+}
+
+// Epilogue for 8 consecutive columns of one row held as fp32 in x[8].
+template <bool OUT_F32>
+__device__ __forceinline__ void epilogue8(const GemmParams& p, int row, int col, float (&x)[8]) {
+    if (p.bias != nullptr) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+        x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+        x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+    }
+    if constexpr (OUT_F32) {
+        float* d = reinterpret_cast<float*>(p.D) + static_cast<long long>(row) * p.ldd + col;
+        red_add_v4_f32(d, x[0], x[1], x[2], x[3]);
+        red_add_v4_f32(d + 4, x[4], x[5], x[6], x[7]);
+    } else {
+        if (p.drop_scale != 0.0f) {
+            const unsigned long long e8 =
+                (static_cast<unsigned long long>(row) * static_cast<unsigned>(p.N) + col) >> 3;
+            const uint32_t keep = dropout_keep8(p.drop_seed, p.drop_stream, e8, p.drop_thresh16);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = ((keep >> i) & 1u) ? x[i] * p.drop_scale : 0.0f;
+        }
+        if (p.addend != nullptr) {
+            const uint4 a = ldg_v4(p.addend + static_cast<long long>(row) * p.ld_add + col);
+            const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z),
+                         a3 = unpack_bf16x2(a.w);
+            x[0] += a0.x; x[1] += a0.y; x[2] += a1.x; x[3] += a1.y;
+            x[4] += a2.x; x[5] += a2.y; x[6] += a3.x; x[7] += a3.y;
+        }
+        bf16* d = reinterpret_cast<bf16*>(p.D) + static_cast<long long>(row) * p.ldd + col;
+        if (p.epilogue == VB_EPI_GELU) {
+            // D <- u (kept for backward), aux_out <- gelu(u) (operand of the next GEMM)
+            uint4 u;
+            u.x = pack_bf16x2(x[0], x[1]); u.y = pack_bf16x2(x[2], x[3]);
+            u.z = pack_bf16x2(x[4], x[5]); u.w = pack_bf16x2(x[6], x[7]);
+            stg_v4(d, u);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = gelu_fwd(x[i]);
+            d = p.aux_out + static_cast<long long>(row) * p.ld_aux + col;
+        } else if (p.epilogue == VB_EPI_DGELU) {
+            const uint4 a = ldg_v4(p.aux_in + static_cast<long long>(row) * p.ld_aux + col);
+            const float2 u0 = unpack_bf16x2(a.x), u1 = unpack_bf16x2(a.y), u2 = unpack_bf16x2(a.z),
+                         u3 = unpack_bf16x2(a.w);
+            x[0] *= gelu_bwd(u0.x); x[1] *= gelu_bwd(u0.y); x[2] *= gelu_bwd(u1.x); x[3] *= gelu_bwd(u1.y);
+            x[4] *= gelu_bwd(u2.x); x[5] *= gelu_bwd(u2.y); x[6] *= gelu_bwd(u3.x); x[7] *= gelu_bwd(u3.y);
+        }
+        uint4 o;
+        o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
+        o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
+        stg_v4(d, o);
+    }
+}
+
+template <bool A_MN, bool B_MN, int BLOCK_N, bool OUT_F32>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmParams p) {
+    using C = Cfg<BLOCK_N>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1 KB alignment
+    uint8_t* smem = smem_raw + (base - raw);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    auto a_tile = [&](int s) { return base + s * C::STAGE_BYTES; };
+    auto b_tile = [&](int s) { return base + s * C::STAGE_BYTES + C::A_BYTES; };
+    auto full_bar = [&](int s) { return base + C::BAR_OFF + 8 * s; };
+    auto empty_bar = [&](int s) { return base + C::BAR_OFF + 8 * (kStages + s); };
+    auto tfull_bar = [&](int s) { return base + C::BAR_OFF + 8 * (2 * kStages + s); };
+    auto tempty_bar = [&](int s) { return base + C::BAR_OFF + 8 * (2 * kStages + 2 + s); };
+    volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + C::TMEM_PTR_OFF);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), kEpiWarps * 32);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(base + C::TMEM_PTR_OFF, C::TMEM_COLS);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
+    const int n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
+    const int k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+    const int num_tiles = m_blocks * n_blocks * p.splits;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------- TMA producer ----------------
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const TileCoord tc = decode_tile(t, n_blocks, p.splits, k_blocks);
+                for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                    if constexpr (!A_MN) {
+                        tma_load_2d(a_tile(stage), &tmA, full_bar(stage), kb * BLOCK_K, tc.m_blk * BLOCK_M);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < BLOCK_M / 64; ++i)
+                            tma_load_2d(a_tile(stage) + i * kAtomBytes, &tmA, full_bar(stage),
+                                        tc.m_blk * BLOCK_M + i * 64, kb * BLOCK_K);
+                    }
+                    if constexpr (!B_MN) {
+                        tma_load_2d(b_tile(stage), &tmB, full_bar(stage), kb * BLOCK_K, tc.n_blk * BLOCK_N);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < BLOCK_N / 64; ++i)
+                            tma_load_2d(b_tile(stage) + i * kAtomBytes, &tmB, full_bar(stage),
+                                        tc.n_blk * BLOCK_N + i * 64, kb * BLOCK_K);
+                    }
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---------------- MMA issuer ----------------
+            constexpr uint32_t idesc = make_idesc(BLOCK_N, A_MN, B_MN);
+            // K-major: advance 16 elements (32 B) inside the swizzle row; MN-major: 16 k-rows (2 KB)
+            constexpr uint32_t a_kstep = A_MN ? UMMA_K * 128 : UMMA_K * 2;
+            constexpr uint32_t b_kstep = B_MN ? UMMA_K * 128 : UMMA_K * 2;
+            constexpr uint32_t a_lbo = A_MN ? kAtomBytes : 0;
+            constexpr uint32_t b_lbo = B_MN ? kAtomBytes : 0;
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+                const TileCoord tc = decode_tile(t, n_blocks, p.splits, k_blocks);
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tcgen05_fence_after();
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t ad = make_smem_desc(a_tile(stage) + k * a_kstep, a_lbo, 1024);
+                        const uint64_t bd = make_smem_desc(b_tile(stage) + k * b_kstep, b_lbo, 1024);
+                        umma_bf16(d_tmem, ad, bd, idesc, (kb > tc.kb_begin || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+                    if (kb == tc.kb_end - 1) umma_commit(tfull_bar(acc));
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ---------------- epilogue ----------------
+        const int ew = warp - 4;
+        const int q = warp & 3;   // TMEM lane quarter this warp may access
+        const int half = ew >> 2; // which half of the tile's columns
+        int it = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            const TileCoord tc = decode_tile(t, n_blocks, p.splits, k_blocks);
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tcgen05_fence_after();
+            const int row = tc.m_blk * BLOCK_M + q * 32 + lane;
+            const int col0 = tc.n_blk * BLOCK_N + half * (BLOCK_N / 2);
+            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N +
+                                    half * (BLOCK_N / 2);
+            // bias belongs to the whole sum: with split-K only split 0 adds it
+            GemmParams pl = p;
+            if (p.splits > 1 && (t % p.splits) != 0) pl.bias = nullptr;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 2; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(taddr0 + c, v);
+                tmem_ld_wait();
+                if (row < p.M) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int col = col0 + c + j * 8;
+                        if (col < p.N) {
+                            float x[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[j * 8 + i]);
+                            epilogue8<OUT_F32>(pl, row, col, x);
+                        }
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            mbar_arrive(tempty_bar(acc));
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+// 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows of stride ld elements;
+// box = 64 x box_outer, 128-byte swizzle, out-of-bounds reads return zero.
+int make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                   uint32_t box_outer) {
+    EncodeTiledFn fn = get_encode_fn();
+    VB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled unavailable (driver too old / no GPU?)");
+    VB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand not 16-byte aligned");
+    VB_REQUIRE((ld_elems * 2) % 16 == 0, "TMA operand row stride must be a multiple of 8 elements");
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {ld_elems * 2};
+    cuuint32_t box[2] = {64, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+    return 0;
+}
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <bool A_MN, bool B_MN, int BLOCK_N, bool OUT_F32>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+    using C = Cfg<BLOCK_N>;
+    auto kern = gemm_tcgen05_kernel<A_MN, B_MN, BLOCK_N, OUT_F32>;
+    static bool configured = false;
+    if (!configured) {
+        VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        configured = true;
+    }
+    const int m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
+    const int n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
+    const int tiles = m_blocks * n_blocks * p.splits;
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    kern<<<grid, kThreads, C::SMEM_BYTES, st>>>(ta, tb, p);
+    g_launches.fetch_add(1);
+    VB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int gemm(const vb_gemm_args& a, cudaStream_t st) {
+    VB_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "vb_gemm: empty problem M=%d N=%d K=%d", a.M, a.N, a.K);
+    VB_REQUIRE(a.N % 8 == 0, "vb_gemm: N=%d must be a multiple of 8", a.N);
+    VB_REQUIRE(a.A && a.B && a.D, "vb_gemm: null operand");
+    VB_REQUIRE(a.ldd % 8 == 0, "vb_gemm: ldd must be a multiple of 8");
+    VB_REQUIRE(a.epilogue == VB_EPI_NONE || a.epilogue == VB_EPI_GELU || a.epilogue == VB_EPI_DGELU,
+               "vb_gemm: unknown epilogue %d", a.epilogue);
+    VB_REQUIRE(a.epilogue != VB_EPI_GELU || a.aux_out, "vb_gemm: GELU epilogue needs aux_out");
+    VB_REQUIRE(a.epilogue != VB_EPI_DGELU || a.aux_in, "vb_gemm: DGELU epilogue needs aux_in");
+    VB_REQUIRE(!a.d_fp32 || (a.epilogue == VB_EPI_NONE && !a.addend && a.dropout_p == 0.0f),
+               "vb_gemm: fp32-accumulate output supports bias only");
+    VB_REQUIRE(a.dropout_p >= 0.0f && a.dropout_p < 1.0f, "vb_gemm: dropout_p out of range");
+
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = a.M; p.N = a.N; p.K = a.K;
+    const int k_blocks = (a.K + BLOCK_K - 1) / BLOCK_K;
+    int splits = (a.d_fp32 && a.splits > 1) ? a.splits : 1;
+    if (splits > k_blocks) splits = k_blocks;
+    p.splits = splits;
+    p.D = a.D; p.ldd = a.ldd;
+    p.bias = a.bias;
+    p.addend = static_cast<const bf16*>(a.addend); p.ld_add = a.ld_add;
+    p.epilogue = a.epilogue;
+    p.aux_in = static_cast<const bf16*>(a.aux_in);
+    p.aux_out = static_cast<bf16*>(a.aux_out);
+    p.ld_aux = a.ld_aux;
+    if (a.dropout_p > 0.0f) {
+        p.drop_scale = 1.0f / (1.0f - a.dropout_p);
+        p.drop_thresh16 = static_cast<unsigned>(a.dropout_p * 65536.0f + 0.5f);
+        p.drop_seed = a.dropout_seed;
+        p.drop_stream = a.dropout_stream;
+    }
+
+    // BLOCK_N: 256 unless N is small or the 256-wide tiling wastes > 25 % of the last tile
+    const bool bn256 = (a.N >= 256) && ((a.N % 256 == 0) || (a.N % 256 > 192));
+    const int BN = bn256 ? 256 : 128;
+
+    CUtensorMap ta, tb;
+    int rc;
+    if (!a.a_mn_major) rc = make_tmap_bf16(&ta, a.A, a.K, a.M, a.lda, BLOCK_M);
+    else               rc = make_tmap_bf16(&ta, a.A, a.M, a.K, a.lda, BLOCK_K);
+    if (rc) return rc;
+    if (!a.b_mn_major) rc = make_tmap_bf16(&tb, a.B, a.K, a.N, a.ldb, BN);
+    else               rc = make_tmap_bf16(&tb, a.B, a.N, a.K, a.ldb, BLOCK_K);
+    if (rc) return rc;
+
+#define VB_DISPATCH(AM, BM, F32)                                         \
+    (bn256 ? launch<AM, BM, 256, F32>(ta, tb, p, st) : launch<AM, BM, 128, F32>(ta, tb, p, st))
+    if (!a.d_fp32) {
+        if (!a.a_mn_major && !a.b_mn_major) return VB_DISPATCH(false, false, false);
+        if (!a.a_mn_major && a.b_mn_major) return VB_DISPATCH(false, true, false);
+        if (a.a_mn_major && a.b_mn_major) return VB_DISPATCH(true, true, false);
+        return VB_DISPATCH(true, false, false);
+    } else {
+        if (!a.a_mn_major && !a.b_mn_major) return VB_DISPATCH(false, false, true);
+        if (!a.a_mn_major && a.b_mn_major) return VB_DISPATCH(false, true, true);
+        if (a.a_mn_major && a.b_mn_major) return VB_DISPATCH(true, true, true);
+        return VB_DISPATCH(true, false, true);
+    }
+#undef VB_DISPATCH
+}
+
+}  // namespace vb
+
+extern "C" {
+int vb_abi_version(void) { return VB_ABI_VERSION; }
+const char* vb_last_error(void) { return vb::get_error(); }
+int64_t vb_launch_count(void) { return vb::g_launches.load(); }
+int vb_gemm(const vb_gemm_args* args, void* stream) {
+    if (!args) { vb::set_error("vb_gemm: null args"); return 2; }
+    return vb::gemm(*args, static_cast<cudaStream_t>(stream));
+}
+}
