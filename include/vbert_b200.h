@@ -61,6 +61,127 @@ typedef struct {
 
 int vb_gemm(const vb_gemm_args* args, void* stream);
 
+/* ---- BertLayerNorm (M.py:162-175) -------------------------------------------------------- */
+/* y = gamma * (x - mean) / sqrt(var + eps) + beta over the last dim; x, y bf16 [rows, hidden];
+ * mean / rstd (fp32 [rows]) are written when non-NULL (saved for backward). */
+int vb_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta, void* y, int64_t ldy,
+                     float* mean, float* rstd, int32_t rows, int32_t hidden, float eps, void* stream);
+/* dx = LN'(dy); dgamma/dbeta/dbias (fp32 [hidden]) are ACCUMULATED; dbias = column sum of the
+ * gradient entering the Linear in front of the LayerNorm. With dropout_p > 0, dx_drop receives
+ * dx * keep/(1-p) (gradient through the hidden dropout of M.py:272/317) and dbias sums dx_drop.
+ * in_dropout_p > 0 re-applies the keep mask of a dropout that FOLLOWED the LayerNorm (M.py:1256). */
+int vb_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                     void* dx, void* dx_drop, float* dgamma, float* dbeta, float* dbias, int32_t rows,
+                     int32_t hidden, float dropout_p, uint64_t dropout_seed, uint32_t dropout_stream,
+                     float in_dropout_p, uint32_t in_dropout_stream, void* stream);
+
+/* ---- BertSelfAttention core (M.py:241-256) ----------------------------------------------- */
+/* qkv bf16 [batch*seq, 3*hidden] (Q | K | V), mask_bias fp32 [batch, seq] additive key bias,
+ * ctx bf16 [batch*seq, hidden], lse fp32 [batch, heads, seq]. head_dim must be 64. */
+int vb_attention_fwd(const void* qkv, const float* mask_bias, void* ctx, float* lse, int32_t batch, int32_t seq,
+                     int32_t heads, int32_t hidden, float dropout_p, uint64_t dropout_seed, uint32_t dropout_stream,
+                     void* stream);
+/* dqkv bf16 [batch*seq, 3*hidden] out; drow fp32 [batch, heads, seq] scratch. */
+int vb_attention_bwd(const void* qkv, const float* mask_bias, const void* ctx, const float* lse, const void* dctx,
+                     void* dqkv, float* drow, int32_t batch, int32_t seq, int32_t heads, int32_t hidden,
+                     float dropout_p, uint64_t dropout_seed, uint32_t dropout_stream, void* stream);
+
+/* ---- helpers ----------------------------------------------------------------------------- */
+/* (1 - cat(input_mask, image_mask)) * -10000 -> fp32 [batch, text+regions]  (M.py:1417, 1286-1294);
+ * masks are int64 as the reference dataloaders produce them; image_mask may be NULL (all ones). */
+int vb_mask_bias(const int64_t* input_mask, const int64_t* image_mask, float* out, int32_t batch, int32_t text_len,
+                 int32_t num_regions, void* stream);
+int vb_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream); /* n % 8 == 0 */
+int vb_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream);
+int vb_colsum_bf16(const void* x, int64_t ld, float* out, int32_t rows, int32_t cols, void* stream); /* out += */
+
+/* ---- BertLayer (M.py:322-341) ------------------------------------------------------------ */
+typedef struct {
+    int32_t batch, seq, hidden, heads, inter;
+    float hidden_dropout, attn_dropout; /* 0 in eval mode */
+    uint64_t seed;                      /* dropout seed of this step */
+    uint32_t layer_index;               /* selects the dropout streams of this layer */
+    /* bf16 compute copies of the nn.Linear weights ([out, in]) */
+    const void* w_qkv;      /* [3H, H]: query | key | value rows (M.py:219-221) */
+    const void* w_attn_out; /* [H, H]   attention.output.dense   (M.py:266) */
+    const void* w_inter;    /* [I, H]   intermediate.dense       (M.py:298) */
+    const void* w_out;      /* [H, I]   output.dense             (M.py:311) */
+    /* fp32 vectors */
+    const float* b_qkv;     /* [3H] */
+    const float* b_attn_out; const float* ln1_gamma; const float* ln1_beta; /* [H] */
+    const float* b_inter;   /* [I] */
+    const float* b_out; const float* ln2_gamma; const float* ln2_beta;      /* [H] */
+    const float* mask_bias; /* [batch, seq] */
+} vb_layer_desc;
+
+/* activations written by forward and consumed by backward; M = batch*seq rows, bf16 unless noted */
+typedef struct {
+    void* qkv;   /* [M, 3H] */
+    void* ctx;   /* [M, H]  */
+    float* lse;  /* [batch, heads, seq] fp32 */
+    void* pre1;  /* [M, H]  attention.output.dense(ctx) (+dropout) + x          (M.py:271-273 before LN) */
+    float* mean1; float* rstd1; /* [M] fp32 */
+    void* x1;    /* [M, H]  attention output = LN(pre1) */
+    void* u;     /* [M, I]  intermediate.dense(x1) before gelu */
+    void* g;     /* [M, I]  gelu(u) */
+    void* pre2;  /* [M, H]  output.dense(g) (+dropout) + x1                      (M.py:316-318 before LN) */
+    float* mean2; float* rstd2;
+} vb_layer_acts;
+
+/* fp32 parameter-gradient accumulators (+=), nn.Linear layout */
+typedef struct {
+    float* dw_qkv; float* db_qkv; float* dw_attn_out; float* db_attn_out; float* dln1_gamma; float* dln1_beta;
+    float* dw_inter; float* db_inter; float* dw_out; float* db_out; float* dln2_gamma; float* dln2_beta;
+} vb_layer_grads;
+
+/* backward scratch, bf16 unless noted */
+typedef struct {
+    void* d_pre;      /* [M, H] */
+    void* d_pre_drop; /* [M, H], only touched when hidden_dropout > 0 */
+    void* d_big;      /* [M, max(I, 3H)] */
+    void* d_x1;       /* [M, H] */
+    void* d_ctx;      /* [M, H] */
+    float* drow;      /* [batch, heads, seq] fp32 */
+} vb_layer_scratch;
+
+/* x_in, x_out: bf16 [M, H]. x_out = BertLayer(x_in). */
+int vb_layer_fwd(const vb_layer_desc* d, const void* x_in, void* x_out, const vb_layer_acts* acts, void* stream);
+/* dy: gradient w.r.t. x_out; dx: gradient w.r.t. x_in (may alias dy). */
+int vb_layer_bwd(const vb_layer_desc* d, const void* x_in, const vb_layer_acts* acts, const void* dy, void* dx,
+                 const vb_layer_grads* grads, const vb_layer_scratch* scratch, void* stream);
+
+/* ---- BertEmbeddingsWithVisualEmbedding (M.py:1169-1257) ----------------------------------- */
+typedef struct {
+    int32_t batch, text_len, num_regions, hidden, visual_dim, vocab, max_pos, n_types;
+    float eps, dropout; uint64_t seed;
+    const int64_t* input_ids;      /* [batch, text_len] */
+    const int64_t* token_type_ids; /* [batch, text_len] */
+    const int64_t* visual_type;    /* [batch, num_regions] */
+    const void* visual_feats;      /* bf16 [batch*num_regions, visual_dim] */
+    const void* w_proj;            /* bf16 [hidden, visual_dim]  projection.weight */
+    const float* b_proj;           /* [hidden] */
+    const float* word; const float* pos; const float* type; const float* pos_vis; const float* type_vis; /* fp32 tables */
+    const float* gamma; const float* beta;
+} vb_embed_desc;
+
+typedef struct {
+    void* vis_proj; /* bf16 [batch*num_regions, hidden] scratch: projection output */
+    void* pre;      /* bf16 [M, hidden] pre-LayerNorm sum (saved) */
+    float* mean; float* rstd; /* [M] */
+} vb_embed_acts;
+
+typedef struct {
+    float* dword; float* dpos; float* dtype; float* dpos_vis; float* dtype_vis; /* fp32 tables, += */
+    float* dw_proj; float* db_proj; float* dgamma; float* dbeta;
+    void* d_pre;  /* bf16 [M, hidden] scratch */
+    void* d_vis;  /* bf16 [batch*num_regions, hidden] scratch */
+    void* d_feats; /* bf16 [batch*num_regions, visual_dim] or NULL: gradient w.r.t. the region features */
+} vb_embed_grads;
+
+/* y: bf16 [M, hidden] = dropout(LN(cat(text, visual))) */
+int vb_embed_fwd(const vb_embed_desc* d, void* y, const vb_embed_acts* acts, void* stream);
+int vb_embed_bwd(const vb_embed_desc* d, const vb_embed_acts* acts, const void* dy, const vb_embed_grads* g, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,87 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every symbol the header declares,
+the ctypes mirrors match the C struct sizes, and the product path refuses to run without CUDA (no CPU fallback)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from visualbert_b200 import _lib
+    L = _lib.lib()
+    header = open(os.path.join(ROOT, "include", "vbert_b200.h")).read()
+    declared = set(re.findall(r"\b(vb_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.vb_abi_version() == 1
+    assert L.vb_launch_count() == 0
+
+
+def test_struct_mirrors_match_c_sizes(tmp_path):
+    from visualbert_b200 import _lib
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "vbert_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(vb_gemm_args),sizeof(vb_layer_desc),sizeof(vb_layer_acts),sizeof(vb_layer_grads),'
+                   'sizeof(vb_layer_scratch),sizeof(vb_embed_desc),sizeof(vb_embed_acts),sizeof(vb_embed_grads));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    mirrors = [_lib.GemmArgs, _lib.LayerDesc, _lib.LayerActs, _lib.LayerGrads, _lib.LayerScratch, _lib.EmbedDesc,
+               _lib.EmbedActs, _lib.EmbedGrads]
+    assert sizes == [ctypes.sizeof(m) for m in mirrors]
+
+
+def test_argument_validation_reports_through_vb_last_error():
+    from visualbert_b200 import _lib
+    L = _lib.lib()
+    a = _lib.GemmArgs()  # all zero: empty problem
+    rc = L.vb_gemm(ctypes.byref(a), None)
+    assert rc != 0
+    assert b"empty problem" in L.vb_last_error()
+    assert L.vb_gemm(None, None) != 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_product_path_fails_loudly_without_cuda():
+    from visualbert_b200 import BertConfig, TrainVisualBERTObjective, _lib, synthetic
+    cfg = BertConfig.from_dict(synthetic.bert_config_dict(1, 128, 2, 512, vocab=64))
+    model = TrainVisualBERTObjective(cfg, "nlvr", visual_embedding_dim=64).eval()
+    batch = synthetic.make_batch(2, 6, 3, 64, head="nlvr", vocab=64)
+    with pytest.raises(_lib.VBertLibraryError):
+        model(**batch)
+
+
+def test_config_round_trip(tmp_path):
+    from visualbert_b200 import BertConfig
+    c = BertConfig(30522, hidden_size=768)
+    p = tmp_path / "bert_config.json"
+    p.write_text(c.to_json_string())
+    c2 = BertConfig.from_json_file(str(p))
+    assert c2.to_dict() == c.to_dict()
+    assert BertConfig(str(p)).hidden_size == 768
+    with pytest.raises(ValueError):
+        BertConfig(3.5)
+
+
+def test_from_pretrained_local_directory(tmp_path):
+    from visualbert_b200 import BertConfig, TrainVisualBERTObjective, synthetic
+    cfgd = synthetic.bert_config_dict(1, 128, 2, 512, vocab=64)
+    (tmp_path / "bert_config.json").write_text(BertConfig.from_dict(cfgd).to_json_string())
+    m = TrainVisualBERTObjective.from_pretrained(str(tmp_path), random_initialize=True, training_head_type="pretraining",
+                                                 visual_embedding_dim=64)
+    sd = {k: v + 1 for k, v in m.state_dict().items()}
+    sd["bert.embeddings.LayerNorm.gamma"] = sd.pop("bert.embeddings.LayerNorm.weight")  # TF-era name (M.py:556-568)
+    torch.save(sd, str(tmp_path / "pytorch_model.bin"))
+    m2 = TrainVisualBERTObjective.from_pretrained(str(tmp_path), training_head_type="pretraining", visual_embedding_dim=64)
+    for k, v in m.state_dict().items():
+        assert torch.allclose(m2.state_dict()[k], v + 1), k
+    m.bert.embeddings.special_intialize()
+    assert torch.equal(m.bert.embeddings.token_type_embeddings_visual.weight, m.bert.embeddings.token_type_embeddings.weight)
+    with pytest.raises(EnvironmentError):
+        TrainVisualBERTObjective.from_pretrained("bert-base-uncased", training_head_type="nlvr")

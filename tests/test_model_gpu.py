@@ -1,0 +1,142 @@
+"""End-to-end parity of the CUDA path (visualbert_b200.TrainVisualBERTObjective -> C ABI -> sm_100a kernels) against
+(a) the committed reference outputs in tests/golden/ (generated from the unmodified reference, fp32 CPU) and
+(b) the oracle (oracle/vb_oracle.py) run in fp32 on the same seeded weights and batches.
+
+Stated bf16 tolerance (activations and GEMM operands are bf16, accumulation / LayerNorm / softmax statistics fp32):
+  loss           |rel err| <= 1e-2
+  logits/hidden  max-abs err <= 5e-2 * max|reference|
+  gradients      per-tensor cosine >= 0.99 and norm ratio within 6 % (tensors whose reference norm is above noise)
+The reference's own fp32 target (1e-3 relative) applies to an fp32 compute path; this build computes in bf16 as
+BASELINE.json's north_star specifies ("stated tolerance for bf16")."""
+import numpy as np
+import pytest
+import torch
+
+import golden_util
+import vb_oracle
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["cfg1_pretraining", "small_ragged_pretraining", "small_vqa", "small_nlvr", "small_multichoice",
+         "base3_ragged_pretraining"]
+LOSS_RTOL, ACT_TOL, GRAD_COS, GRAD_NORM = 1e-2, 5e-2, 0.99, 0.06
+
+
+def _build(name, train=False):
+    from visualbert_b200 import BertConfig, TrainVisualBERTObjective
+    cfg, sd, batch, c, gold = golden_util.load(name)
+    dev = torch.device("cuda:0")
+    model = TrainVisualBERTObjective(BertConfig.from_dict(cfg), c["head"], visual_embedding_dim=c["Dv"])
+    res = model.load_state_dict(sd, strict=False)
+    assert set(res.missing_keys) <= {"cls.predictions.decoder.weight"} and not res.unexpected_keys
+    model.to(dev)
+    model.train(train)
+    batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    sd_dev = {k: v.to(dev) for k, v in sd.items()}
+    return model, cfg, sd_dev, batch, c, gold
+
+
+def _relmax(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-12)
+
+
+def test_state_dict_keys_match_reference_layout():
+    from visualbert_b200 import synthetic
+    model, cfg, sd, batch, c, gold = _build("cfg1_pretraining")
+    mine = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    want = synthetic.param_shapes(cfg, c["head"], c["Dv"])
+    want["cls.predictions.decoder.weight"] = want["bert.embeddings.word_embeddings.weight"]
+    assert mine == {k: tuple(v) for k, v in want.items()}
+    assert model.cls.predictions.decoder.weight is model.bert.embeddings.word_embeddings.weight  # tied (M.py:414)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_forward_backward_parity(name):
+    model, cfg, sd, batch, c, gold = _build(name)
+    from visualbert_b200 import _lib
+    n0 = _lib.launch_count()
+    out = model(**batch)
+    assert _lib.launch_count() > n0, "the CUDA library did not launch anything"
+    loss = out["loss"]
+    # (a) reference goldens
+    assert abs(loss.item() - float(gold["loss"])) <= LOSS_RTOL * abs(float(gold["loss"]))
+    assert _relmax(golden_util.subsample(out["logits"].float()), gold["logits_sub"]) < ACT_TOL
+    if "nsp" in gold:
+        assert _relmax(out["seq_relationship_score"].float().cpu().numpy(), gold["nsp"]) < ACT_TOL
+    # (b) oracle on the same device, fp32
+    sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    kw = {k: v for k, v in batch.items() if k != "position_embeddings_visual"}
+    ref = vb_oracle.objective(sdo, cfg, c["head"], **kw)
+    assert abs(loss.item() - ref["loss"].item()) <= LOSS_RTOL * abs(ref["loss"].item())
+    assert _relmax(out["logits"].float().cpu().numpy().reshape(-1), ref["logits"].detach().cpu().numpy().reshape(-1)) < ACT_TOL
+    enc = model(**{**batch, "output_all_encoded_layers": True})
+    assert len(enc["sequence_output"]) == cfg["num_hidden_layers"]
+    last = enc["sequence_output"][-1].float()
+    assert _relmax(last.detach().cpu().numpy(), ref["sequence_output"].detach().cpu().numpy()) < ACT_TOL
+    assert _relmax(golden_util.subsample(last), gold[f"hidden{cfg['num_hidden_layers'] - 1}_sub"]) < ACT_TOL
+    assert _relmax(enc["pooled_output"].float().detach().cpu().numpy(), gold["pooled"]) < ACT_TOL
+    # gradients
+    loss.backward()
+    ref["loss"].backward()
+    gold_norms = dict(zip(gold["grad_names"].tolist(), gold["grad_norms"].tolist()))
+    big = max(gold_norms.values())
+    checked = 0
+    for k, p in model.named_parameters():
+        if k == "cls.predictions.decoder.weight":
+            continue
+        g_ref = sdo[k].grad
+        if g_ref is None:
+            assert p.grad is None or p.grad.abs().max().item() == 0, k
+            continue
+        assert p.grad is not None, f"no gradient for {k}"
+        a, b = p.grad.float().reshape(-1), g_ref.float().reshape(-1)
+        nb = b.norm().item()
+        if nb < 1e-3 * big:  # below bf16 noise floor of this step: only require it to stay small
+            assert a.norm().item() < 3e-3 * big, k
+            continue
+        cos = torch.dot(a, b).item() / max(a.norm().item() * nb, 1e-30)
+        assert cos >= GRAD_COS, f"{k}: cosine {cos:.5f}"
+        assert abs(a.norm().item() / nb - 1.0) <= GRAD_NORM, f"{k}: norm ratio {a.norm().item() / nb:.4f}"
+        assert abs(nb - gold_norms[k]) <= 1e-3 * max(gold_norms[k], 1e-6) + 1e-6, f"oracle grad norm drifted from golden: {k}"
+        checked += 1
+    assert checked >= 10
+
+
+def test_three_d_inputs_are_flattened_like_the_reference():
+    model, cfg, sd, batch, c, gold = _build("small_multichoice")
+    assert batch["input_ids"].dim() == 3 and batch["visual_embeddings"].dim() == 4
+    out = model(**batch)
+    assert out["logits"].shape == (batch["input_ids"].shape[0], 4)
+
+
+def test_train_mode_dropout_is_active_and_seeded():
+    model, cfg, sd, batch, c, gold = _build("base3_ragged_pretraining", train=True)
+    model.bert._step = 0
+    l1 = model(**batch)["loss"].item()
+    model.bert._step = 0
+    l2 = model(**batch)["loss"].item()
+    l3 = model(**batch)["loss"].item()
+    assert l1 == l2, "same seed must reproduce the same dropout masks"
+    assert l1 != l3, "a new step must draw new masks"
+    model.eval()
+    le = model(**batch)["loss"].item()
+    assert abs(l1 - le) > 1e-4
+    # training-mode gradients exist and are finite
+    model.train()
+    model.zero_grad()
+    model(**batch)["loss"].backward()
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            assert torch.isfinite(p.grad).all(), k
+
+
+def test_unsupported_modes_raise_explicitly():
+    from visualbert_b200 import BertConfig, TrainVisualBERTObjective
+    from visualbert_b200 import synthetic
+    cfg = BertConfig.from_dict(synthetic.bert_config_dict(1, 128, 2, 512, vocab=64))
+    with pytest.raises(NotImplementedError):
+        TrainVisualBERTObjective(cfg, "nlvr", visual_embedding_dim=64, output_attention_weights=True)
+    with pytest.raises(NotImplementedError):
+        TrainVisualBERTObjective(BertConfig.from_dict(synthetic.bert_config_dict(1, 128, 2, 512, vocab=64)), "nlvr",
+                                 visual_embedding_dim=64, bypass_transformer=True)

@@ -31,6 +31,43 @@ class GemmArgs(ctypes.Structure):
     ]
 
 
+def _struct(name, fields):
+    return type(name, (ctypes.Structure,), {"_fields_": fields})
+
+
+_P = c_void_p
+LayerDesc = _struct("LayerDesc", [
+    ("batch", c_int), ("seq", c_int), ("hidden", c_int), ("heads", c_int), ("inter", c_int),
+    ("hidden_dropout", c_f32), ("attn_dropout", c_f32), ("seed", c_u64), ("layer_index", c_u32),
+    ("w_qkv", _P), ("w_attn_out", _P), ("w_inter", _P), ("w_out", _P),
+    ("b_qkv", _P), ("b_attn_out", _P), ("ln1_gamma", _P), ("ln1_beta", _P),
+    ("b_inter", _P), ("b_out", _P), ("ln2_gamma", _P), ("ln2_beta", _P), ("mask_bias", _P)])
+LayerActs = _struct("LayerActs", [(n, _P) for n in (
+    "qkv", "ctx", "lse", "pre1", "mean1", "rstd1", "x1", "u", "g", "pre2", "mean2", "rstd2")])
+LayerGrads = _struct("LayerGrads", [(n, _P) for n in (
+    "dw_qkv", "db_qkv", "dw_attn_out", "db_attn_out", "dln1_gamma", "dln1_beta",
+    "dw_inter", "db_inter", "dw_out", "db_out", "dln2_gamma", "dln2_beta")])
+LayerScratch = _struct("LayerScratch", [(n, _P) for n in ("d_pre", "d_pre_drop", "d_big", "d_x1", "d_ctx", "drow")])
+EmbedDesc = _struct("EmbedDesc", [
+    ("batch", c_int), ("text_len", c_int), ("num_regions", c_int), ("hidden", c_int), ("visual_dim", c_int),
+    ("vocab", c_int), ("max_pos", c_int), ("n_types", c_int),
+    ("eps", c_f32), ("dropout", c_f32), ("seed", c_u64),
+    ("input_ids", _P), ("token_type_ids", _P), ("visual_type", _P), ("visual_feats", _P),
+    ("w_proj", _P), ("b_proj", _P),
+    ("word", _P), ("pos", _P), ("type", _P), ("pos_vis", _P), ("type_vis", _P), ("gamma", _P), ("beta", _P)])
+EmbedActs = _struct("EmbedActs", [(n, _P) for n in ("vis_proj", "pre", "mean", "rstd")])
+EmbedGrads = _struct("EmbedGrads", [(n, _P) for n in (
+    "dword", "dpos", "dtype", "dpos_vis", "dtype_vis", "dw_proj", "db_proj", "dgamma", "dbeta",
+    "d_pre", "d_vis", "d_feats")])
+
+# every symbol include/vbert_b200.h declares (checked by tests/test_abi.py without a GPU)
+EXPORTS = [
+    "vb_abi_version", "vb_last_error", "vb_launch_count", "vb_gemm", "vb_layernorm_fwd", "vb_layernorm_bwd",
+    "vb_attention_fwd", "vb_attention_bwd", "vb_mask_bias", "vb_cast_f32_to_bf16", "vb_cast_bf16_to_f32",
+    "vb_colsum_bf16", "vb_layer_fwd", "vb_layer_bwd", "vb_embed_fwd", "vb_embed_bwd",
+]
+
+
 class VBertLibraryError(RuntimeError):
     pass
 

@@ -8,10 +8,17 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
 
 namespace vb {
 
 typedef __nv_bfloat16 bf16;
+
+// host-side shared state / helpers (defined in vb_gemm.cu)
+extern std::atomic<long long> g_launches;  // kernel launches issued by this library
+int num_sms();
 
 // ---------------------------------------------------------------------------------------------
 // error plumbing (host)
@@ -245,6 +252,17 @@ __device__ __forceinline__ uint4 ldg_v4(const void* p) {
     return __ldg(reinterpret_cast<const uint4*>(p));
 }
 __device__ __forceinline__ void stg_v4(void* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
+// 256-bit global access (sm_100): one full 32-byte sector per thread per instruction
+__device__ __forceinline__ void ldg_v8(const void* p, uint32_t (&r)[8]) {
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void stg_v8(void* p, const uint32_t (&r)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
 __device__ __forceinline__ void red_add_v4_f32(float* p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c),
                  "f"(d)

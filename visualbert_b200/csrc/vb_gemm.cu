@@ -111,55 +111,70 @@ __device__ __forceinline__ TileCoord decode_tile(int t, int n_blocks, int splits
     return c;
 }
 
-// Epilogue for 8 consecutive columns of one row held as fp32 in x[8].
+// Epilogue for 16 consecutive columns of one row held as fp32 in x[16]. All global traffic is
+// 32 bytes per thread per access (256-bit LDG/STG): a thread owns a row, so 32-byte pieces are the
+// unit that keeps every DRAM/L2 sector fully written.
+__device__ __forceinline__ void load16_bf16(const bf16* p, float (&f)[16]) {
+    uint32_t r[8];
+    ldg_v8(p, r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float2 t = unpack_bf16x2(r[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ void store16_bf16(bf16* p, const float (&f)[16]) {
+    uint32_t r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+    stg_v8(p, r);
+}
+
 template <bool OUT_F32>
-__device__ __forceinline__ void epilogue8(const GemmParams& p, int row, int col, float (&x)[8]) {
+__device__ __forceinline__ void epilogue16(const GemmParams& p, int row, int col, float (&x)[16]) {
     if (p.bias != nullptr) {
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-        x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-        x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4 * i));
+            x[4 * i] += b.x; x[4 * i + 1] += b.y; x[4 * i + 2] += b.z; x[4 * i + 3] += b.w;
+        }
     }
     if constexpr (OUT_F32) {
         float* d = reinterpret_cast<float*>(p.D) + static_cast<long long>(row) * p.ldd + col;
-        red_add_v4_f32(d, x[0], x[1], x[2], x[3]);
-        red_add_v4_f32(d + 4, x[4], x[5], x[6], x[7]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) red_add_v4_f32(d + 4 * i, x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
     } else {
         if (p.drop_scale != 0.0f) {
             const unsigned long long e8 =
                 (static_cast<unsigned long long>(row) * static_cast<unsigned>(p.N) + col) >> 3;
-            const uint32_t keep = dropout_keep8(p.drop_seed, p.drop_stream, e8, p.drop_thresh16);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = ((keep >> i) & 1u) ? x[i] * p.drop_scale : 0.0f;
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t keep = dropout_keep8(p.drop_seed, p.drop_stream, e8 + h, p.drop_thresh16);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[8 * h + i] = ((keep >> i) & 1u) ? x[8 * h + i] * p.drop_scale : 0.0f;
+            }
         }
         if (p.addend != nullptr) {
-            const uint4 a = ldg_v4(p.addend + static_cast<long long>(row) * p.ld_add + col);
-            const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z),
-                         a3 = unpack_bf16x2(a.w);
-            x[0] += a0.x; x[1] += a0.y; x[2] += a1.x; x[3] += a1.y;
-            x[4] += a2.x; x[5] += a2.y; x[6] += a3.x; x[7] += a3.y;
+            float a[16];
+            load16_bf16(p.addend + static_cast<long long>(row) * p.ld_add + col, a);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] += a[i];
         }
         bf16* d = reinterpret_cast<bf16*>(p.D) + static_cast<long long>(row) * p.ldd + col;
         if (p.epilogue == VB_EPI_GELU) {
             // D <- u (kept for backward), aux_out <- gelu(u) (operand of the next GEMM)
-            uint4 u;
-            u.x = pack_bf16x2(x[0], x[1]); u.y = pack_bf16x2(x[2], x[3]);
-            u.z = pack_bf16x2(x[4], x[5]); u.w = pack_bf16x2(x[6], x[7]);
-            stg_v4(d, u);
+            store16_bf16(d, x);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = gelu_fwd(x[i]);
+            for (int i = 0; i < 16; ++i) x[i] = gelu_fwd(x[i]);
             d = p.aux_out + static_cast<long long>(row) * p.ld_aux + col;
         } else if (p.epilogue == VB_EPI_DGELU) {
-            const uint4 a = ldg_v4(p.aux_in + static_cast<long long>(row) * p.ld_aux + col);
-            const float2 u0 = unpack_bf16x2(a.x), u1 = unpack_bf16x2(a.y), u2 = unpack_bf16x2(a.z),
-                         u3 = unpack_bf16x2(a.w);
-            x[0] *= gelu_bwd(u0.x); x[1] *= gelu_bwd(u0.y); x[2] *= gelu_bwd(u1.x); x[3] *= gelu_bwd(u1.y);
-            x[4] *= gelu_bwd(u2.x); x[5] *= gelu_bwd(u2.y); x[6] *= gelu_bwd(u3.x); x[7] *= gelu_bwd(u3.y);
+            float u[16];
+            load16_bf16(p.aux_in + static_cast<long long>(row) * p.ld_aux + col, u);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] *= gelu_bwd(u[i]);
         }
-        uint4 o;
-        o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
-        o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
-        stg_v4(d, o);
+        store16_bf16(d, x);
     }
 }
 
@@ -300,13 +315,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 tmem_ld_wait();
                 if (row < p.M) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int col = col0 + c + j * 8;
+                    for (int j = 0; j < 2; ++j) {
+                        const int col = col0 + c + j * 16;
                         if (col < p.N) {
-                            float x[8];
+                            float x[16];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[j * 8 + i]);
-                            epilogue8<OUT_F32>(pl, row, col, x);
+                            for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[j * 16 + i]);
+                            epilogue16<OUT_F32>(pl, row, col, x);
                         }
                     }
                 }
@@ -397,9 +412,11 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
 
 int gemm(const vb_gemm_args& a, cudaStream_t st) {
     VB_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "vb_gemm: empty problem M=%d N=%d K=%d", a.M, a.N, a.K);
-    VB_REQUIRE(a.N % 8 == 0, "vb_gemm: N=%d must be a multiple of 8", a.N);
+    VB_REQUIRE(a.N % 16 == 0, "vb_gemm: N=%d must be a multiple of 16", a.N);
     VB_REQUIRE(a.A && a.B && a.D, "vb_gemm: null operand");
-    VB_REQUIRE(a.ldd % 8 == 0, "vb_gemm: ldd must be a multiple of 8");
+    VB_REQUIRE(a.ldd % 16 == 0 && (reinterpret_cast<uintptr_t>(a.D) & 31) == 0, "vb_gemm: D must be 32-byte aligned with ldd a multiple of 16");
+    VB_REQUIRE(!a.addend || (a.ld_add % 16 == 0 && (reinterpret_cast<uintptr_t>(a.addend) & 31) == 0), "vb_gemm: addend must be 32-byte aligned with ld a multiple of 16");
+    VB_REQUIRE((!a.aux_in && !a.aux_out) || a.ld_aux % 16 == 0, "vb_gemm: ld_aux must be a multiple of 16");
     VB_REQUIRE(a.epilogue == VB_EPI_NONE || a.epilogue == VB_EPI_GELU || a.epilogue == VB_EPI_DGELU,
                "vb_gemm: unknown epilogue %d", a.epilogue);
     VB_REQUIRE(a.epilogue != VB_EPI_GELU || a.aux_out, "vb_gemm: GELU epilogue needs aux_out");

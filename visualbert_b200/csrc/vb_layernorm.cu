@@ -1,0 +1,257 @@
+// vb_layernorm.cu — BertLayerNorm forward / backward (reference modeling.py:162-175: TF style,
+// biased variance, eps inside the sqrt, statistics in fp32) for bf16 activations.
+//
+// HBM-bound row kernels: one warp per row, the row lives in registers (16-byte loads, lane l owns
+// column chunks l, l+32, ...), warp-shuffle reductions, no shared memory in forward. Backward also
+// produces the column reductions a fused residual block needs in the same pass: dgamma, dbeta and
+// the bias gradient of the Linear that precedes the LayerNorm (column sum of the output gradient),
+// accumulated in registers across a grid-stride row loop, reduced through shared memory and flushed
+// with one fp32 atomic per column per block.
+#include "../../include/vbert_b200.h"
+#include "vb_common.cuh"
+
+namespace vb {
+
+constexpr int kLnWarps = 8;
+
+template <int NC>
+__global__ void __launch_bounds__(kLnWarps * 32)
+ln_fwd_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+              const float* __restrict__ beta, bf16* __restrict__ y, long long ldy, float* __restrict__ mean_out,
+              float* __restrict__ rstd_out, int rows, int H, float eps) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kLnWarps + warp;
+    if (row >= rows) return;
+    const int chunks = H >> 3;
+    float v[NC][8];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const int ch = lane + c * 32;
+        if (ch < chunks) {
+            const uint4 u = ldg_v4(x + row * ldx + ch * 8);
+            const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), d = unpack_bf16x2(u.z), e = unpack_bf16x2(u.w);
+            v[c][0] = a.x; v[c][1] = a.y; v[c][2] = b.x; v[c][3] = b.y;
+            v[c][4] = d.x; v[c][5] = d.y; v[c][6] = e.x; v[c][7] = e.y;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s += v[c][i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[c][i] = 0.f;
+        }
+    }
+    const float mean = warp_sum(s) / H;
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        if (lane + c * 32 < chunks) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float d = v[c][i] - mean; q += d * d; }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / H + eps);
+    if (lane == 0) {
+        if (mean_out) mean_out[row] = mean;
+        if (rstd_out) rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const int ch = lane + c * 32;
+        if (ch < chunks) {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8 + 4));
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + ch * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + ch * 8 + 4));
+            const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = g[i] * ((v[c][i] - mean) * rstd) + b[i];
+            uint4 u;
+            u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
+            u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+            stg_v4(y + row * ldy + ch * 8, u);
+        }
+    }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma,  xhat = (x - mean) * rstd
+// dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy ; dbias += sum_rows dx_out
+// where dx_out = dx (no dropout) or dx * keep / (1-p) (the gradient entering the preceding Linear
+// when its output went through dropout before the residual add; dx itself continues down the
+// residual branch).
+template <int NC>
+__global__ void __launch_bounds__(kLnWarps * 32)
+ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean,
+              const float* __restrict__ rstd, const float* __restrict__ gamma, bf16* __restrict__ dx,
+              bf16* __restrict__ dx_drop, float* __restrict__ dgamma, float* __restrict__ dbeta,
+              float* __restrict__ dbias, int rows, int H, float drop_scale, unsigned drop_thresh16,
+              unsigned long long drop_seed, unsigned drop_stream, float in_scale, unsigned in_thresh16,
+              unsigned in_stream) {
+    extern __shared__ float red[];  // [3][H]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunks = H >> 3;
+    for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+
+    float gam[NC][8], ag[NC][8], ab[NC][8], ad[NC][8];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const int ch = lane + c * 32;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            gam[c][i] = (ch < chunks) ? __ldg(gamma + ch * 8 + i) : 0.f;
+            ag[c][i] = ab[c][i] = ad[c][i] = 0.f;
+        }
+    }
+    const float invH = 1.0f / H;
+    for (int row = blockIdx.x * kLnWarps + warp; row < rows; row += gridDim.x * kLnWarps) {
+        const float mu = mean[row], rs = rstd[row];
+        float xh[NC][8], g[NC][8];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const int ch = lane + c * 32;
+            if (ch < chunks) {
+                const uint4 ux = ldg_v4(x + static_cast<long long>(row) * H + ch * 8);
+                const uint4 ud = ldg_v4(dy + static_cast<long long>(row) * H + ch * 8);
+                const float2 x0 = unpack_bf16x2(ux.x), x1 = unpack_bf16x2(ux.y), x2 = unpack_bf16x2(ux.z), x3 = unpack_bf16x2(ux.w);
+                const float2 d0 = unpack_bf16x2(ud.x), d1 = unpack_bf16x2(ud.y), d2 = unpack_bf16x2(ud.z), d3 = unpack_bf16x2(ud.w);
+                const float xv[8] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y, x3.x, x3.y};
+                float dv[8] = {d0.x, d0.y, d1.x, d1.y, d2.x, d2.y, d3.x, d3.y};
+                if (in_scale != 0.f) {  // dy is the gradient of dropout(LN(x)): re-apply the keep mask
+                    const unsigned long long e8 = (static_cast<unsigned long long>(row) * static_cast<unsigned>(H) + ch * 8) >> 3;
+                    const uint32_t keep = dropout_keep8(drop_seed, in_stream, e8, in_thresh16);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dv[i] = ((keep >> i) & 1u) ? dv[i] * in_scale : 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    xh[c][i] = (xv[i] - mu) * rs;
+                    g[c][i] = dv[i] * gam[c][i];
+                    s1 += g[c][i];
+                    s2 += g[c][i] * xh[c][i];
+                    ag[c][i] += dv[i] * xh[c][i];
+                    ab[c][i] += dv[i];
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { xh[c][i] = 0.f; g[c][i] = 0.f; }
+            }
+        }
+        const float c1 = warp_sum(s1) * invH, c2 = warp_sum(s2) * invH;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const int ch = lane + c * 32;
+            if (ch < chunks) {
+                float o[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = rs * (g[c][i] - c1 - xh[c][i] * c2);
+                uint4 u;
+                u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
+                u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+                stg_v4(dx + static_cast<long long>(row) * H + ch * 8, u);
+                if (dx_drop != nullptr) {
+                    const unsigned long long e8 = (static_cast<unsigned long long>(row) * static_cast<unsigned>(H) + ch * 8) >> 3;
+                    const uint32_t keep = dropout_keep8(drop_seed, drop_stream, e8, drop_thresh16);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] = ((keep >> i) & 1u) ? o[i] * drop_scale : 0.f;
+                    u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
+                    u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+                    stg_v4(dx_drop + static_cast<long long>(row) * H + ch * 8, u);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) ad[c][i] += o[i];
+            }
+        }
+    }
+    // block reduction through shared memory, then one global atomic per column
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const int ch = lane + c * 32;
+        if (ch < chunks) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                atomicAdd(&red[ch * 8 + i], ag[c][i]);
+                atomicAdd(&red[H + ch * 8 + i], ab[c][i]);
+                atomicAdd(&red[2 * H + ch * 8 + i], ad[c][i]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < H; i += blockDim.x) {
+        if (dgamma) atomicAdd(dgamma + i, red[i]);
+        if (dbeta) atomicAdd(dbeta + i, red[H + i]);
+        if (dbias) atomicAdd(dbias + i, red[2 * H + i]);
+    }
+}
+
+int ln_fwd(const void* x, long long ldx, const float* gamma, const float* beta, void* y, long long ldy,
+           float* mean, float* rstd, int rows, int H, float eps, cudaStream_t st) {
+    VB_REQUIRE(H % 8 == 0 && H <= 1024 * 2, "layernorm: H=%d must be a multiple of 8 and <= 2048", H);
+    VB_REQUIRE(rows > 0, "layernorm: no rows");
+    const int nc = (H / 8 + 31) / 32;
+    const int grid = (rows + kLnWarps - 1) / kLnWarps;
+    const bf16* xb = static_cast<const bf16*>(x);
+    bf16* yb = static_cast<bf16*>(y);
+#define VB_LN_FWD(NC) ln_fwd_kernel<NC><<<grid, kLnWarps * 32, 0, st>>>(xb, ldx, gamma, beta, yb, ldy, mean, rstd, rows, H, eps)
+    switch (nc) {
+        case 1: VB_LN_FWD(1); break;
+        case 2: VB_LN_FWD(2); break;
+        case 3: VB_LN_FWD(3); break;
+        case 4: VB_LN_FWD(4); break;
+        default: VB_LN_FWD(8); break;
+    }
+#undef VB_LN_FWD
+    g_launches.fetch_add(1);
+    VB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
+           void* dx_drop, float* dgamma, float* dbeta, float* dbias, int rows, int H, float dropout_p,
+           unsigned long long seed, unsigned stream_id, float in_dropout_p, unsigned in_stream_id, cudaStream_t st) {
+    VB_REQUIRE(H % 8 == 0 && H <= 1024, "layernorm backward: H=%d must be a multiple of 8 and <= 1024", H);
+    VB_REQUIRE(rows > 0, "layernorm backward: no rows");
+    VB_REQUIRE((dropout_p > 0.f) == (dx_drop != nullptr), "layernorm backward: dx_drop iff dropout_p > 0");
+    const int nc = (H / 8 + 31) / 32;
+    int grid = num_sms() * 4;
+    const int need = (rows + kLnWarps - 1) / kLnWarps;
+    if (grid > need) grid = need;
+    const float scale = dropout_p > 0.f ? 1.0f / (1.0f - dropout_p) : 0.f;
+    const unsigned th = static_cast<unsigned>(dropout_p * 65536.0f + 0.5f);
+    const float in_scale = in_dropout_p > 0.f ? 1.0f / (1.0f - in_dropout_p) : 0.f;
+    const unsigned in_th = static_cast<unsigned>(in_dropout_p * 65536.0f + 0.5f);
+    const size_t smem = 3 * H * sizeof(float);
+#define VB_LN_BWD(NC)                                                                                        \
+    ln_bwd_kernel<NC><<<grid, kLnWarps * 32, smem, st>>>(                                                    \
+        static_cast<const bf16*>(dy), static_cast<const bf16*>(x), mean, rstd, gamma, static_cast<bf16*>(dx), \
+        static_cast<bf16*>(dx_drop), dgamma, dbeta, dbias, rows, H, scale, th, seed, stream_id, in_scale,    \
+        in_th, in_stream_id)
+    switch (nc) {
+        case 1: VB_LN_BWD(1); break;
+        case 2: VB_LN_BWD(2); break;
+        case 3: VB_LN_BWD(3); break;
+        default: VB_LN_BWD(4); break;
+    }
+#undef VB_LN_BWD
+    g_launches.fetch_add(1);
+    VB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace vb
+
+extern "C" {
+int vb_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta, void* y, int64_t ldy,
+                     float* mean, float* rstd, int32_t rows, int32_t hidden, float eps, void* stream) {
+    return vb::ln_fwd(x, ldx, gamma, beta, y, ldy, mean, rstd, rows, hidden, eps, static_cast<cudaStream_t>(stream));
+}
+int vb_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                     void* dx, void* dx_drop, float* dgamma, float* dbeta, float* dbias, int32_t rows,
+                     int32_t hidden, float dropout_p, uint64_t dropout_seed, uint32_t dropout_stream,
+                     float in_dropout_p, uint32_t in_dropout_stream, void* stream) {
+    return vb::ln_bwd(dy, x, mean, rstd, gamma, dx, dx_drop, dgamma, dbeta, dbias, rows, hidden, dropout_p,
+                      dropout_seed, dropout_stream, in_dropout_p, in_dropout_stream, static_cast<cudaStream_t>(stream));
+}
+}

@@ -1,0 +1,299 @@
+"""torch.autograd bindings of the libvbert_b200 C ABI (include/vbert_b200.h).
+
+PyTorch supplies device memory, the current stream and the autograd graph; every FLOP of the
+encoder path runs in the sm_100a kernels. There is no fallback: on a machine without the library or
+without a CUDA device these ops raise.
+
+Activations are bf16; parameters are the model's fp32 master weights, cast to bf16 "compute weights"
+by vb_cast_f32_to_bf16 (cached per parameter version). Parameter gradients come back in fp32.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_BF16 = torch.bfloat16
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise _lib.VBertLibraryError(
+            f"{what}: tensor is on {t.device}; visualbert_b200 runs only on CUDA (sm_100a) — no CPU fallback")
+
+
+# --------------------------------------------------------------------------------------------
+# workspaces: backward scratch is shared by all layers of a step (same stream, sequential use)
+# --------------------------------------------------------------------------------------------
+_scratch_cache = {}
+
+
+def _scratch(dev, M, H, I, B, A, S, need_drop):
+    key = (dev, M, H, I, B, A, S)
+    w = _scratch_cache.get(key)
+    if w is None:
+        w = dict(
+            d_pre=torch.empty(M, H, device=dev, dtype=_BF16),
+            d_pre_drop=None,
+            d_big=torch.empty(M, max(I, 3 * H), device=dev, dtype=_BF16),
+            d_x1=torch.empty(M, H, device=dev, dtype=_BF16),
+            d_ctx=torch.empty(M, H, device=dev, dtype=_BF16),
+            drow=torch.empty(B, A, S, device=dev, dtype=torch.float32))
+        _scratch_cache.clear()  # keep a single shape resident
+        _scratch_cache[key] = w
+    if need_drop and w["d_pre_drop"] is None:
+        w["d_pre_drop"] = torch.empty(M, H, device=dev, dtype=_BF16)
+    return w
+
+
+def cast_to_bf16(src, out=None):
+    """fp32 -> bf16 through vb_cast_f32_to_bf16 (numel must be a multiple of 8)."""
+    _require_cuda(src, "cast_to_bf16")
+    src = src.contiguous()
+    if out is None:
+        out = torch.empty(src.shape, device=src.device, dtype=_BF16)
+    _lib.check(_lib.lib().vb_cast_f32_to_bf16(ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                              ctypes.c_int64(src.numel()), _stream()), "vb_cast_f32_to_bf16")
+    return out
+
+
+def mask_bias(input_mask, image_mask):
+    """(1 - cat(input_mask, image_mask)) * -10000 as fp32 [B, T+V] (reference M.py:1417, 1286-1294)."""
+    _require_cuda(input_mask, "mask_bias")
+    B, T = input_mask.shape
+    V = 0 if image_mask is None else image_mask.shape[1]
+    im = input_mask.to(torch.int64).contiguous()
+    vm = None if image_mask is None else image_mask.to(torch.int64).contiguous()
+    out = torch.empty(B, T + V, device=input_mask.device, dtype=torch.float32)
+    _lib.check(_lib.lib().vb_mask_bias(ctypes.c_void_p(im.data_ptr()), ctypes.c_void_p(_ptr(vm)),
+                                       ctypes.c_void_p(out.data_ptr()), B, T, V, _stream()), "vb_mask_bias")
+    return out
+
+
+class LayerWeights:
+    """bf16 compute copies of one BertLayer's matrices, refreshed when the fp32 masters change."""
+
+    def __init__(self):
+        self.key = None
+        self.buf = None
+
+    def get(self, q, k, v, o, w1, w2, bq, bk, bv):
+        key = tuple((p.data_ptr(), p._version) for p in (q, k, v, o, w1, w2, bq, bk, bv))
+        if key != self.key:
+            H, I = o.shape[0], w1.shape[0]
+            dev = q.device
+            if self.buf is None or self.buf[0].device != dev:
+                self.buf = (torch.empty(3 * H, H, device=dev, dtype=_BF16), torch.empty(H, H, device=dev, dtype=_BF16),
+                            torch.empty(I, H, device=dev, dtype=_BF16), torch.empty(H, I, device=dev, dtype=_BF16),
+                            torch.empty(3 * H, device=dev, dtype=torch.float32))
+            wqkv, wo, wi, wout, bqkv = self.buf
+            with torch.no_grad():
+                cast_to_bf16(q.detach(), wqkv[0:H])
+                cast_to_bf16(k.detach(), wqkv[H:2 * H])
+                cast_to_bf16(v.detach(), wqkv[2 * H:3 * H])
+                cast_to_bf16(o.detach(), wo)
+                cast_to_bf16(w1.detach(), wi)
+                cast_to_bf16(w2.detach(), wout)
+                torch.cat((bq.detach(), bk.detach(), bv.detach()), out=bqkv)
+            self.key = key
+        return self.buf
+
+
+class _LayerFn(torch.autograd.Function):
+    """BertLayer forward/backward (reference M.py:322-341) through vb_layer_fwd / vb_layer_bwd."""
+
+    @staticmethod
+    def forward(ctx, x, mbias, meta, qw, qb, kw, kb, vw, vb, ow, ob, g1, b1, iw, ib, dw, db, g2, b2):
+        # meta: dict(heads, layer_index, hidden_dropout, attn_dropout, seed, cache=LayerWeights)
+        _require_cuda(x, "bert_layer")
+        B, S, H = x.shape
+        I = iw.shape[0]
+        M = B * S
+        A = meta["heads"]
+        dev = x.device
+        x = x.contiguous()
+        wqkv, wo, wi, wout, bqkv = meta["cache"].get(qw, kw, vw, ow, iw, dw, qb, kb, vb)
+        f32 = torch.float32
+        acts = dict(
+            qkv=torch.empty(M, 3 * H, device=dev, dtype=_BF16), ctx=torch.empty(M, H, device=dev, dtype=_BF16),
+            lse=torch.empty(B, A, S, device=dev, dtype=f32), pre1=torch.empty(M, H, device=dev, dtype=_BF16),
+            mean1=torch.empty(M, device=dev, dtype=f32), rstd1=torch.empty(M, device=dev, dtype=f32),
+            x1=torch.empty(M, H, device=dev, dtype=_BF16), u=torch.empty(M, I, device=dev, dtype=_BF16),
+            g=torch.empty(M, I, device=dev, dtype=_BF16), pre2=torch.empty(M, H, device=dev, dtype=_BF16),
+            mean2=torch.empty(M, device=dev, dtype=f32), rstd2=torch.empty(M, device=dev, dtype=f32))
+        y = torch.empty(B, S, H, device=dev, dtype=_BF16)
+        d = _lib.LayerDesc(
+            batch=B, seq=S, hidden=H, heads=A, inter=I, hidden_dropout=meta["hidden_dropout"],
+            attn_dropout=meta["attn_dropout"], seed=meta["seed"], layer_index=meta["layer_index"],
+            w_qkv=wqkv.data_ptr(), w_attn_out=wo.data_ptr(), w_inter=wi.data_ptr(), w_out=wout.data_ptr(),
+            b_qkv=bqkv.data_ptr(), b_attn_out=ob.data_ptr(), ln1_gamma=g1.data_ptr(), ln1_beta=b1.data_ptr(),
+            b_inter=ib.data_ptr(), b_out=db.data_ptr(), ln2_gamma=g2.data_ptr(), ln2_beta=b2.data_ptr(),
+            mask_bias=mbias.data_ptr())
+        a = _lib.LayerActs(**{k: t.data_ptr() for k, t in acts.items()})
+        _lib.check(_lib.lib().vb_layer_fwd(ctypes.byref(d), ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(y.data_ptr()),
+                                           ctypes.byref(a), _stream()), "vb_layer_fwd")
+        ctx.meta = meta
+        ctx.acts = acts
+        ctx.weights = (wqkv, wo, wi, wout, bqkv)
+        ctx.weight_key = meta["cache"].key
+        ctx.save_for_backward(x, mbias, ob, g1, b1, ib, db, g2, b2)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mbias, ob, g1, b1, ib, db, g2, b2 = ctx.saved_tensors
+        meta, acts = ctx.meta, ctx.acts
+        if meta["cache"].key != ctx.weight_key:
+            raise RuntimeError("visualbert_b200: layer weights were modified between forward and backward")
+        wqkv, wo, wi, wout, bqkv = ctx.weights
+        B, S, H = x.shape
+        I = wi.shape[0]
+        M, A = B * S, meta["heads"]
+        dev = x.device
+        dy = dy.to(_BF16).contiguous()
+        sizes = [3 * H * H, 3 * H, H * H, H, H, H, I * H, I, H * I, H, H, H]
+        flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
+        parts = list(torch.split(flat, sizes))
+        gnames = ("dw_qkv", "db_qkv", "dw_attn_out", "db_attn_out", "dln1_gamma", "dln1_beta",
+                  "dw_inter", "db_inter", "dw_out", "db_out", "dln2_gamma", "dln2_beta")
+        g = _lib.LayerGrads(**{n: t.data_ptr() for n, t in zip(gnames, parts)})
+        hd = meta["hidden_dropout"] > 0
+        w = _scratch(dev, M, H, I, B, A, S, hd)
+        sc = _lib.LayerScratch(**{k: _ptr(t) for k, t in w.items()})
+        d = _lib.LayerDesc(
+            batch=B, seq=S, hidden=H, heads=A, inter=I, hidden_dropout=meta["hidden_dropout"],
+            attn_dropout=meta["attn_dropout"], seed=meta["seed"], layer_index=meta["layer_index"],
+            w_qkv=wqkv.data_ptr(), w_attn_out=wo.data_ptr(), w_inter=wi.data_ptr(), w_out=wout.data_ptr(),
+            b_qkv=bqkv.data_ptr(), b_attn_out=ob.data_ptr(), ln1_gamma=g1.data_ptr(), ln1_beta=b1.data_ptr(),
+            b_inter=ib.data_ptr(), b_out=db.data_ptr(), ln2_gamma=g2.data_ptr(), ln2_beta=b2.data_ptr(),
+            mask_bias=mbias.data_ptr())
+        a = _lib.LayerActs(**{k: t.data_ptr() for k, t in acts.items()})
+        dx = torch.empty(B, S, H, device=dev, dtype=_BF16)
+        _lib.check(_lib.lib().vb_layer_bwd(ctypes.byref(d), ctypes.c_void_p(x.data_ptr()), ctypes.byref(a),
+                                           ctypes.c_void_p(dy.data_ptr()), ctypes.c_void_p(dx.data_ptr()),
+                                           ctypes.byref(g), ctypes.byref(sc), _stream()), "vb_layer_bwd")
+        ctx.acts = None
+        dwqkv, dbqkv, dwo, dbo, dg1, db1, dwi, dbi, dwout, dbout, dg2, db2 = parts
+        dwq, dwk, dwv = dwqkv.view(3, H, H).unbind(0)
+        dbq, dbk, dbv = dbqkv.view(3, H).unbind(0)
+        return (dx, None, None, dwq, dbq, dwk, dbk, dwv, dbv, dwo.view(H, H), dbo, dg1, db1,
+                dwi.view(I, H), dbi, dwout.view(H, I), dbout, dg2, db2)
+
+
+def bert_layer(x, mbias, meta, params):
+    """params: the 16 tensors of one BertLayer in reference order (q.w, q.b, k.w, k.b, v.w, v.b, attention.output
+    dense.w/.b, LayerNorm.w/.b, intermediate.dense.w/.b, output.dense.w/.b, LayerNorm.w/.b)."""
+    return _LayerFn.apply(x, mbias, meta, *params)
+
+
+class ProjectionWeights:
+    def __init__(self):
+        self.key = None
+        self.buf = None
+
+    def get(self, w):
+        key = (w.data_ptr(), w._version)
+        if key != self.key:
+            with torch.no_grad():
+                self.buf = cast_to_bf16(w.detach(), self.buf if self.buf is not None and self.buf.device == w.device else None)
+            self.key = key
+        return self.buf
+
+
+class _EmbedFn(torch.autograd.Function):
+    """BertEmbeddingsWithVisualEmbedding.forward (reference M.py:1198-1257) through vb_embed_fwd / vb_embed_bwd."""
+
+    @staticmethod
+    def forward(ctx, meta, input_ids, token_type_ids, visual_type, feats, word, pos, typ, typ_vis, pos_vis, pw, pb, gamma, beta):
+        _require_cuda(word, "bert_embeddings")
+        dev = word.device
+        B, T = input_ids.shape
+        V = 0 if feats is None else feats.shape[1]
+        H = word.shape[1]
+        M = B * (T + V)
+        ids = input_ids.to(torch.int64).contiguous()
+        tt = token_type_ids.to(torch.int64).contiguous()
+        if V > 0:
+            Dv = feats.shape[2]
+            vt = visual_type.to(torch.int64).contiguous()
+            f = feats.reshape(B * V, Dv)
+            fb = cast_to_bf16(f) if f.dtype == torch.float32 else f.to(_BF16).contiguous()
+            wp = meta["cache"].get(pw)
+            vis_proj = torch.empty(B * V, H, device=dev, dtype=_BF16)
+        else:
+            Dv, vt, fb, wp, vis_proj = 0, None, None, None, None
+        pre = torch.empty(M, H, device=dev, dtype=_BF16)
+        mean = torch.empty(M, device=dev, dtype=torch.float32)
+        rstd = torch.empty(M, device=dev, dtype=torch.float32)
+        y = torch.empty(B, T + V, H, device=dev, dtype=_BF16)
+        d = _lib.EmbedDesc(
+            batch=B, text_len=T, num_regions=V, hidden=H, visual_dim=Dv, vocab=word.shape[0], max_pos=pos.shape[0],
+            n_types=typ.shape[0], eps=1e-12, dropout=meta["dropout"], seed=meta["seed"],
+            input_ids=ids.data_ptr(), token_type_ids=tt.data_ptr(), visual_type=_ptr(vt), visual_feats=_ptr(fb),
+            w_proj=_ptr(wp), b_proj=_ptr(pb), word=word.data_ptr(), pos=pos.data_ptr(), type=typ.data_ptr(),
+            pos_vis=pos_vis.data_ptr(), type_vis=typ_vis.data_ptr(), gamma=gamma.data_ptr(), beta=beta.data_ptr())
+        a = _lib.EmbedActs(vis_proj=_ptr(vis_proj), pre=pre.data_ptr(), mean=mean.data_ptr(), rstd=rstd.data_ptr())
+        _lib.check(_lib.lib().vb_embed_fwd(ctypes.byref(d), ctypes.c_void_p(y.data_ptr()), ctypes.byref(a), _stream()),
+                   "vb_embed_fwd")
+        ctx.meta = meta
+        ctx.shape = (B, T, V, H, Dv)
+        ctx.feats_need_grad = feats is not None and feats.requires_grad
+        ctx.feats_dtype = None if feats is None else feats.dtype
+        ctx.feats_shape = None if feats is None else feats.shape
+        ctx.save_for_backward(ids, tt, vt, fb, wp, pb, word, pos, typ, typ_vis, pos_vis, gamma, beta, pre, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        ids, tt, vt, fb, wp, pb, word, pos, typ, typ_vis, pos_vis, gamma, beta, pre, mean, rstd = ctx.saved_tensors
+        B, T, V, H, Dv = ctx.shape
+        meta = ctx.meta
+        dev = word.device
+        M = B * (T + V)
+        dy = dy.to(_BF16).contiguous()
+        f32 = torch.float32
+        dword = torch.zeros_like(word, dtype=f32)
+        dpos = torch.zeros_like(pos, dtype=f32)
+        dtyp = torch.zeros_like(typ, dtype=f32)
+        dtyp_vis = torch.zeros_like(typ_vis, dtype=f32)
+        dpos_vis = torch.zeros_like(pos_vis, dtype=f32)
+        dgamma = torch.zeros_like(gamma, dtype=f32)
+        dbeta = torch.zeros_like(beta, dtype=f32)
+        d_pre = torch.empty(M, H, device=dev, dtype=_BF16)
+        if V > 0:
+            dpw = torch.zeros(H, Dv, device=dev, dtype=f32)
+            dpb = torch.zeros(H, device=dev, dtype=f32)
+            d_vis = torch.empty(B * V, H, device=dev, dtype=_BF16)
+            d_feats = torch.empty(B * V, Dv, device=dev, dtype=_BF16) if ctx.feats_need_grad else None
+        else:
+            dpw = dpb = d_vis = d_feats = None
+        d = _lib.EmbedDesc(
+            batch=B, text_len=T, num_regions=V, hidden=H, visual_dim=Dv, vocab=word.shape[0], max_pos=pos.shape[0],
+            n_types=typ.shape[0], eps=1e-12, dropout=meta["dropout"], seed=meta["seed"],
+            input_ids=ids.data_ptr(), token_type_ids=tt.data_ptr(), visual_type=_ptr(vt), visual_feats=_ptr(fb),
+            w_proj=_ptr(wp), b_proj=_ptr(pb), word=word.data_ptr(), pos=pos.data_ptr(), type=typ.data_ptr(),
+            pos_vis=pos_vis.data_ptr(), type_vis=typ_vis.data_ptr(), gamma=gamma.data_ptr(), beta=beta.data_ptr())
+        a = _lib.EmbedActs(vis_proj=0, pre=pre.data_ptr(), mean=mean.data_ptr(), rstd=rstd.data_ptr())
+        g = _lib.EmbedGrads(
+            dword=dword.data_ptr(), dpos=dpos.data_ptr(), dtype=dtyp.data_ptr(), dpos_vis=dpos_vis.data_ptr(),
+            dtype_vis=dtyp_vis.data_ptr(), dw_proj=_ptr(dpw), db_proj=_ptr(dpb), dgamma=dgamma.data_ptr(),
+            dbeta=dbeta.data_ptr(), d_pre=d_pre.data_ptr(), d_vis=_ptr(d_vis), d_feats=_ptr(d_feats))
+        _lib.check(_lib.lib().vb_embed_bwd(ctypes.byref(d), ctypes.byref(a), ctypes.c_void_p(dy.data_ptr()),
+                                           ctypes.byref(g), _stream()), "vb_embed_bwd")
+        dfe = None
+        if d_feats is not None:
+            dfe = d_feats.view(ctx.feats_shape).to(ctx.feats_dtype)
+        return (None, None, None, None, dfe, dword, dpos, dtyp, dtyp_vis, dpos_vis, dpw, dpb, dgamma, dbeta)
+
+
+def bert_embeddings(meta, input_ids, token_type_ids, visual_type, feats, word, pos, typ, typ_vis, pos_vis, pw, pb, gamma, beta):
+    return _EmbedFn.apply(meta, input_ids, token_type_ids, visual_type, feats, word, pos, typ, typ_vis, pos_vis, pw, pb,
+                          gamma, beta)
