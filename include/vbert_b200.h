@@ -30,6 +30,12 @@ int vb_abi_version(void);
 const char* vb_last_error(void);
 /* number of kernel launches issued by this library on the calling process since load */
 int64_t vb_launch_count(void);
+/* Live profiling: when enabled every launcher brackets its kernels with CUDA events on the launch stream.
+ * vb_profile_read synchronises the device and returns, per category (0 GEMM/tcgen05, 1 attention,
+ * 2 row-wise HBM-bound kernels, 3 other), the summed kernel time [ms], the algorithmic work (FLOPs for
+ * 0-1, bytes for 2-3) and the number of launches since the previous read; arrays of 4. */
+void vb_profile_enable(int on);
+int vb_profile_read(double* ms, double* work, int64_t* launches);
 
 /* ---- GEMM core (tcgen05.mma + TMA + TMEM) ------------------------------------------------ */
 /* epilogue selectors */

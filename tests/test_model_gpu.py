@@ -63,13 +63,13 @@ def test_forward_backward_parity(name):
     assert abs(loss.item() - float(gold["loss"])) <= LOSS_RTOL * abs(float(gold["loss"]))
     assert _relmax(golden_util.subsample(out["logits"].float()), gold["logits_sub"]) < ACT_TOL
     if "nsp" in gold:
-        assert _relmax(out["seq_relationship_score"].float().cpu().numpy(), gold["nsp"]) < ACT_TOL
+        assert _relmax(out["seq_relationship_score"].detach().float().cpu().numpy(), gold["nsp"]) < ACT_TOL
     # (b) oracle on the same device, fp32
     sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     kw = {k: v for k, v in batch.items() if k != "position_embeddings_visual"}
     ref = vb_oracle.objective(sdo, cfg, c["head"], **kw)
     assert abs(loss.item() - ref["loss"].item()) <= LOSS_RTOL * abs(ref["loss"].item())
-    assert _relmax(out["logits"].float().cpu().numpy().reshape(-1), ref["logits"].detach().cpu().numpy().reshape(-1)) < ACT_TOL
+    assert _relmax(out["logits"].detach().float().cpu().numpy().reshape(-1), ref["logits"].detach().cpu().numpy().reshape(-1)) < ACT_TOL
     enc = model(**{**batch, "output_all_encoded_layers": True})
     assert len(enc["sequence_output"]) == cfg["num_hidden_layers"]
     last = enc["sequence_output"][-1].float()

@@ -1,0 +1,71 @@
+"""world_size-2 gloo test of the data-parallel plumbing (no GPU): FlatGradSync's single all-reduce equals
+single-process gradients on the concatenated batch when each rank holds the same number of loss terms."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from visualbert_b200.parallel import FlatGradSync, shard_batch
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 3))
+    model[2].weight = model[2].weight  # no-op; keeps parameters() order deterministic
+    x = torch.randn(12, 8); y = torch.randn(12, 3)
+    sync = FlatGradSync(model)
+    calls = []
+    orig = dist.all_reduce
+    dist.all_reduce = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    sync.zero()
+    b = shard_batch({"x": x, "y": y, "tag": "keep"}, rank, world)
+    assert b["tag"] == "keep" and b["x"].shape[0] == 6
+    torch.nn.functional.mse_loss(model(b["x"]), b["y"]).backward()
+    flat = sync.allreduce().clone()
+    dist.all_reduce = orig
+    assert len(calls) == 1, "exactly one collective per step"
+    for p in model.parameters():
+        assert p.grad.data_ptr() >= sync.flat.data_ptr()  # grads live inside the flat buffer
+    if rank == 0:
+        ref = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 3))
+        ref.load_state_dict(model.state_dict())
+        torch.nn.functional.mse_loss(ref(x), y).backward()
+        want = torch.cat([p.grad.reshape(-1) for p in ref.parameters()])
+        q.put(float((flat - want).abs().max()))
+    dist.destroy_process_group()
+
+
+def test_flat_grad_allreduce_matches_single_process():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) < 1e-6
+
+
+def test_flat_grad_sync_single_process_and_tied_weights():
+    sys.path.insert(0, ROOT)
+    from visualbert_b200.parallel import FlatGradSync
+    emb = torch.nn.Embedding(10, 4)
+    dec = torch.nn.Linear(4, 10, bias=False)
+    dec.weight = emb.weight
+    m = torch.nn.ModuleList([emb, dec])
+    s = FlatGradSync(m)
+    assert s.flat.numel() == 40
+    dec(emb(torch.tensor([1, 2]))).sum().backward()
+    assert s.flat.abs().sum() > 0
+    s.zero()
+    assert s.flat.abs().sum() == 0 and emb.weight.grad is s.views[0]
+    s.allreduce()  # no process group: no-op

@@ -62,7 +62,7 @@ EmbedGrads = _struct("EmbedGrads", [(n, _P) for n in (
 
 # every symbol include/vbert_b200.h declares (checked by tests/test_abi.py without a GPU)
 EXPORTS = [
-    "vb_abi_version", "vb_last_error", "vb_launch_count", "vb_gemm", "vb_layernorm_fwd", "vb_layernorm_bwd",
+    "vb_abi_version", "vb_last_error", "vb_launch_count", "vb_profile_enable", "vb_profile_read", "vb_gemm", "vb_layernorm_fwd", "vb_layernorm_bwd",
     "vb_attention_fwd", "vb_attention_bwd", "vb_mask_bias", "vb_cast_f32_to_bf16", "vb_cast_bf16_to_f32",
     "vb_colsum_bf16", "vb_layer_fwd", "vb_layer_bwd", "vb_embed_fwd", "vb_embed_bwd",
 ]
@@ -99,3 +99,17 @@ def check(rc, what):
 
 def launch_count():
     return int(lib().vb_launch_count())
+
+
+PROFILE_CATEGORIES = ("gemm_tcgen05", "attention", "rowwise", "other")
+
+
+def profile_enable(on=True):
+    lib().vb_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """-> {category: dict(ms, work, launches)} since the previous read (synchronises the device)."""
+    ms = (ctypes.c_double * 4)(); work = (ctypes.c_double * 4)(); n = (ctypes.c_int64 * 4)()
+    check(lib().vb_profile_read(ms, work, n), "vb_profile_read")
+    return {c: dict(ms=ms[i], work=work[i], launches=int(n[i])) for i, c in enumerate(PROFILE_CATEGORIES)}

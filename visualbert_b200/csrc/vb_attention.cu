@@ -525,8 +525,10 @@ int attn_fwd(const void* qkv, const float* mask_bias, void* ctx, float* lse, int
     int rc = fill_params(p, qkv, mask_bias, ctx, lse, nullptr, nullptr, nullptr, B, S, A, H, dropout_p, seed, stream_id);
     if (rc) return rc;
     dim3 grid((S + kBlk - 1) / kBlk, A, B);
-    attn_fwd_kernel<<<grid, 128, 0, st>>>(p);
-    g_launches.fetch_add(1);
+    {
+        ProfScope ps(st, PROF_ATTN, 4.0 * B * A * S * S * kHd, 1);
+        attn_fwd_kernel<<<grid, 128, 0, st>>>(p);
+    }
     VB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -545,9 +547,11 @@ int attn_bwd(const void* qkv, const float* mask_bias, const void* ctx, const flo
         configured = true;
     }
     dim3 grid((S + kBlk - 1) / kBlk, A, B);
-    attn_bwd_dq_kernel<<<grid, 128, 7 * kTileBytes, st>>>(p);
-    attn_bwd_dkv_kernel<<<grid, 128, 6 * kTileBytes, st>>>(p);
-    g_launches.fetch_add(2);
+    {
+        ProfScope ps(st, PROF_ATTN, 8.0 * B * A * S * S * kHd, 2);  // algorithmic: 2x forward
+        attn_bwd_dq_kernel<<<grid, 128, 7 * kTileBytes, st>>>(p);
+        attn_bwd_dkv_kernel<<<grid, 128, 6 * kTileBytes, st>>>(p);
+    }
     VB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

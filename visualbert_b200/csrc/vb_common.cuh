@@ -20,6 +20,16 @@ typedef __nv_bfloat16 bf16;
 extern std::atomic<long long> g_launches;  // kernel launches issued by this library
 int num_sms();
 
+// Optional live profiling (vb_profile_enable): every launcher brackets its kernels with CUDA events on
+// the launch stream and tags them with a category and the algorithmic work (FLOPs or bytes) of the call.
+enum { PROF_GEMM = 0, PROF_ATTN = 1, PROF_ROWWISE = 2, PROF_OTHER = 3, PROF_NCAT = 4 };
+struct ProfScope {
+    ProfScope(cudaStream_t st, int cat, double work, int launches);
+    ~ProfScope();
+    int slot;
+    cudaStream_t st;
+};
+
 // ---------------------------------------------------------------------------------------------
 // error plumbing (host)
 // ---------------------------------------------------------------------------------------------

@@ -228,13 +228,13 @@ int embed_fwd(const EmbedParams& p, cudaStream_t st) {
     const long long rows = static_cast<long long>(p.B) * (p.T + p.V);
     const int grid = static_cast<int>((rows + kEmbWarps - 1) / kEmbWarps);
     const int nc = (p.H / 8 + 31) / 32;
+    ProfScope ps(st, PROF_ROWWISE, 8.0 * rows * p.H, 1);
     switch (nc) {
         case 1: embed_fwd_kernel<1><<<grid, kEmbWarps * 32, 0, st>>>(p); break;
         case 2: embed_fwd_kernel<2><<<grid, kEmbWarps * 32, 0, st>>>(p); break;
         case 3: embed_fwd_kernel<3><<<grid, kEmbWarps * 32, 0, st>>>(p); break;
         default: embed_fwd_kernel<4><<<grid, kEmbWarps * 32, 0, st>>>(p); break;
     }
-    g_launches.fetch_add(1);
     VB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -247,8 +247,10 @@ int embed_bwd(const EmbedBwdParams& p, cudaStream_t st) {
     if (grid > need) grid = static_cast<int>(need);
     const size_t smem = static_cast<size_t>(2 * p.n_types + 1) * p.H * sizeof(float);
     VB_REQUIRE(smem <= 48 * 1024, "embed backward: type_vocab_size * hidden too large for shared memory");
-    embed_bwd_kernel<<<grid, kEmbWarps * 32, smem, st>>>(p);
-    g_launches.fetch_add(1);
+    {
+        ProfScope ps(st, PROF_ROWWISE, 6.0 * rows * p.H, 1);
+        embed_bwd_kernel<<<grid, kEmbWarps * 32, smem, st>>>(p);
+    }
     VB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -256,8 +258,10 @@ int embed_bwd(const EmbedBwdParams& p, cudaStream_t st) {
 int mask_bias(const long long* input_mask, const long long* image_mask, float* out, int B, int T, int V, cudaStream_t st) {
     const long long n = static_cast<long long>(B) * (T + V);
     VB_REQUIRE(n > 0, "mask_bias: empty");
-    mask_bias_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(input_mask, image_mask, out, B, T, V);
-    g_launches.fetch_add(1);
+    {
+        ProfScope ps(st, PROF_OTHER, 12.0 * n, 1);
+        mask_bias_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(input_mask, image_mask, out, B, T, V);
+    }
     VB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -268,8 +272,10 @@ int cast_f32_bf16(const float* src, void* dst, long long n, cudaStream_t st) {
     const long long n8 = n / 8;
     long long blocks = (n8 + 255) / 256;
     if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-    cast_f32_bf16_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(src, static_cast<bf16*>(dst), n8);
-    g_launches.fetch_add(1);
+    {
+        ProfScope ps(st, PROF_OTHER, 6.0 * n, 1);
+        cast_f32_bf16_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(src, static_cast<bf16*>(dst), n8);
+    }
     VB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -279,8 +285,10 @@ int cast_bf16_f32(const void* src, float* dst, long long n, cudaStream_t st) {
     const long long n8 = n / 8;
     long long blocks = (n8 + 255) / 256;
     if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-    cast_bf16_f32_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(static_cast<const bf16*>(src), dst, n8);
-    g_launches.fetch_add(1);
+    {
+        ProfScope ps(st, PROF_OTHER, 6.0 * n, 1);
+        cast_bf16_f32_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(static_cast<const bf16*>(src), dst, n8);
+    }
     VB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -291,8 +299,10 @@ int colsum(const void* x, long long ld, float* out, int M, int N, cudaStream_t s
     int gy = (num_sms() * 4) / gx;
     if (gy < 1) gy = 1;
     if (gy > (M + 7) / 8) gy = (M + 7) / 8;
-    colsum_kernel<<<dim3(gx, gy), dim3(32, 8), 0, st>>>(static_cast<const bf16*>(x), ld, out, M, N);
-    g_launches.fetch_add(1);
+    {
+        ProfScope ps(st, PROF_ROWWISE, 2.0 * M * N, 1);
+        colsum_kernel<<<dim3(gx, gy), dim3(32, 8), 0, st>>>(static_cast<const bf16*>(x), ld, out, M, N);
+    }
     VB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

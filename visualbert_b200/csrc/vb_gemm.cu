@@ -18,6 +18,8 @@
 #include <string.h>
 
 #include <atomic>
+#include <mutex>
+#include <vector>
 
 #include "../../include/vbert_b200.h"
 #include "vb_common.cuh"
@@ -37,6 +39,31 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 const char* get_error() { return g_err; }
+
+// ---- live profiling -------------------------------------------------------------------------
+struct ProfRec { cudaEvent_t e0, e1; int cat; double work; int launches; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;      // records in use
+static std::vector<ProfRec> g_prof_pool; // recycled event pairs
+static std::mutex g_prof_mu;
+
+ProfScope::ProfScope(cudaStream_t s, int cat, double work, int launches) : slot(-1), st(s) {
+    g_launches.fetch_add(launches);
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfRec r;
+    if (!g_prof_pool.empty()) { r = g_prof_pool.back(); g_prof_pool.pop_back(); }
+    else { cudaEventCreate(&r.e0); cudaEventCreate(&r.e1); }
+    r.cat = cat; r.work = work; r.launches = launches;
+    cudaEventRecord(r.e0, st);
+    g_prof.push_back(r);
+    slot = static_cast<int>(g_prof.size()) - 1;
+}
+ProfScope::~ProfScope() {
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEventRecord(g_prof[slot].e1, st);
+}
 
 // ---------------------------------------------------------------------------------------------
 // tile configuration
@@ -404,8 +431,10 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
     const int n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
     const int tiles = m_blocks * n_blocks * p.splits;
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, kThreads, C::SMEM_BYTES, st>>>(ta, tb, p);
-    g_launches.fetch_add(1);
+    {
+        ProfScope ps(st, PROF_GEMM, 2.0 * p.M * p.N * p.K, 1);
+        kern<<<grid, kThreads, C::SMEM_BYTES, st>>>(ta, tb, p);
+    }
     VB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -481,6 +510,23 @@ extern "C" {
 int vb_abi_version(void) { return VB_ABI_VERSION; }
 const char* vb_last_error(void) { return vb::get_error(); }
 int64_t vb_launch_count(void) { return vb::g_launches.load(); }
+void vb_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(vb::g_prof_mu);
+    vb::g_prof_on = on != 0;
+}
+int vb_profile_read(double* ms, double* work, int64_t* launches) {
+    if (cudaDeviceSynchronize() != cudaSuccess) { vb::set_error("vb_profile_read: device sync failed"); return 1; }
+    std::lock_guard<std::mutex> lk(vb::g_prof_mu);
+    for (int c = 0; c < vb::PROF_NCAT; ++c) { ms[c] = 0; work[c] = 0; launches[c] = 0; }
+    for (auto& r : vb::g_prof) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.e0, r.e1);
+        ms[r.cat] += t; work[r.cat] += r.work; launches[r.cat] += r.launches;
+        vb::g_prof_pool.push_back(r);
+    }
+    vb::g_prof.clear();
+    return 0;
+}
 int vb_gemm(const vb_gemm_args* args, void* stream) {
     if (!args) { vb::set_error("vb_gemm: null args"); return 2; }
     return vb::gemm(*args, static_cast<cudaStream_t>(stream));

@@ -194,6 +194,7 @@ int ln_fwd(const void* x, long long ldx, const float* gamma, const float* beta, 
     const int grid = (rows + kLnWarps - 1) / kLnWarps;
     const bf16* xb = static_cast<const bf16*>(x);
     bf16* yb = static_cast<bf16*>(y);
+    ProfScope ps(st, PROF_ROWWISE, 4.0 * rows * H, 1);  // bytes: read + write bf16
 #define VB_LN_FWD(NC) ln_fwd_kernel<NC><<<grid, kLnWarps * 32, 0, st>>>(xb, ldx, gamma, beta, yb, ldy, mean, rstd, rows, H, eps)
     switch (nc) {
         case 1: VB_LN_FWD(1); break;
@@ -203,7 +204,6 @@ int ln_fwd(const void* x, long long ldx, const float* gamma, const float* beta, 
         default: VB_LN_FWD(8); break;
     }
 #undef VB_LN_FWD
-    g_launches.fetch_add(1);
     VB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -223,6 +223,7 @@ int ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, 
     const float in_scale = in_dropout_p > 0.f ? 1.0f / (1.0f - in_dropout_p) : 0.f;
     const unsigned in_th = static_cast<unsigned>(in_dropout_p * 65536.0f + 0.5f);
     const size_t smem = 3 * H * sizeof(float);
+    ProfScope ps(st, PROF_ROWWISE, (dx_drop ? 8.0 : 6.0) * rows * H, 1);
 #define VB_LN_BWD(NC)                                                                                        \
     ln_bwd_kernel<NC><<<grid, kLnWarps * 32, smem, st>>>(                                                    \
         static_cast<const bf16*>(dy), static_cast<const bf16*>(x), mean, rstd, gamma, static_cast<bf16*>(dx), \
@@ -235,7 +236,6 @@ int ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, 
         default: VB_LN_BWD(4); break;
     }
 #undef VB_LN_BWD
-    g_launches.fetch_add(1);
     VB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -197,15 +197,15 @@ class BertEncoder(nn.Module):
 
 
 class BertPooler(nn.Module):
-    """tanh(W h[CLS] + b) (M.py:374-386); tiny, stays PyTorch."""
+    """tanh(W h[CLS] + b) (M.py:374-386); tiny, stays PyTorch and fp32 (returns fp32 like the reference)."""
 
     def __init__(self, config):
         super().__init__()
         self.dense = nn.Linear(config.hidden_size, config.hidden_size)
 
     def forward(self, hidden_states):
-        first = hidden_states[:, 0]
-        return torch.tanh(F.linear(first, self.dense.weight.to(first.dtype), self.dense.bias.to(first.dtype)))
+        first = hidden_states[:, 0].float()  # [B, H]: negligible work, keep the reference's fp32 arithmetic
+        return torch.tanh(F.linear(first, self.dense.weight.float(), self.dense.bias.float()))
 
 
 class BertEmbeddingsWithVisualEmbedding(nn.Module):
@@ -574,7 +574,7 @@ class TrainVisualBERTObjective(PreTrainedBertModel):
 
         if head == "vqa":
             index_to_gather = flat_input_mask.sum(1) - 2  # second-to-last valid text token (M.py:1504)
-            gathered = torch.gather(sequence_output, 1, index_to_gather.view(-1, 1, 1).expand(-1, 1, sequence_output.size(-1)))
+            gathered = torch.gather(sequence_output, 1, index_to_gather.view(-1, 1, 1).expand(-1, 1, sequence_output.size(-1))).float()
             logits = _lin(self.dropout(gathered), self.classifier)
             reshaped_logits = logits.contiguous().view(-1, 3129)
             output_dict["logits"] = logits

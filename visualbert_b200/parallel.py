@@ -1,0 +1,63 @@
+"""Data-parallel plumbing: one process per GPU, replicated weights, and ONE all-reduce
+per step over a flat fp32 gradient buffer — replacing the reference's single-process nn.DataParallel
+(visualbert/models/model_wrapper.py:146: per-step parameter broadcast + gradient reduce to GPU 0).
+
+`FlatGradSync` makes every `p.grad` a view into one contiguous buffer, so the collective needs no
+packing copy; `allreduce()` issues a single `torch.distributed.all_reduce` (NCCL over NVLink on the
+B200 box, gloo in the CPU tests) and divides by the world size, i.e. the mean of per-rank mean losses —
+the same semantics as the reference's `loss.mean()` over DataParallel replicas (model_wrapper.py:75).
+"""
+import torch
+import torch.distributed as dist
+
+
+class FlatGradSync:
+    def __init__(self, module, process_group=None):
+        seen, self.params = set(), []
+        for p in module.parameters():
+            if p.requires_grad and id(p) not in seen:  # tied weights appear once
+                seen.add(id(p))
+                self.params.append(p)
+        if not self.params:
+            raise ValueError("FlatGradSync: module has no trainable parameters")
+        dev = self.params[0].device
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.group = process_group
+        off = 0
+        self.views = []
+        for p in self.params:
+            v = self.flat[off: off + p.numel()].view_as(p)
+            off += p.numel()
+            p.grad = v
+            self.views.append(v)
+
+    def zero(self):
+        """Replaces optimizer.zero_grad(): one memset; re-attaches views a caller may have dropped."""
+        self.flat.zero_()
+        for p, v in zip(self.params, self.views):
+            if p.grad is not v:
+                p.grad = v
+
+    def allreduce(self):
+        """The single collective of the step. No-op for a lone process."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat.div_(dist.get_world_size(self.group))
+        return self.flat
+
+
+def shard_batch(batch, rank, world_size):
+    """Split every tensor of a reference-style batch dict on dim 0 (what DataParallel's scatter did,
+    visualbert/models/train.py:146,179), keeping non-tensors."""
+    out = {}
+    for k, v in batch.items():
+        if torch.is_tensor(v):
+            n = v.shape[0]
+            if n % world_size != 0:
+                raise ValueError(f"batch dim {n} of '{k}' is not divisible by world size {world_size}")
+            per = n // world_size
+            out[k] = v[rank * per: (rank + 1) * per]
+        else:
+            out[k] = v
+    return out
