@@ -85,3 +85,17 @@ def test_from_pretrained_local_directory(tmp_path):
     assert torch.equal(m.bert.embeddings.token_type_embeddings_visual.weight, m.bert.embeddings.token_type_embeddings.weight)
     with pytest.raises(EnvironmentError):
         TrainVisualBERTObjective.from_pretrained("bert-base-uncased", training_head_type="nlvr")
+
+
+def test_lazy_output_dict_defers_and_caches():
+    from visualbert_b200.modeling import LazyOutputDict
+    d, calls = LazyOutputDict(), []
+    d.set_lazy("logits", lambda: (calls.append(1), 42)[1])
+    d["loss"] = 1.5
+    assert "logits" in d and list(d.keys()) == ["logits", "loss"] and not calls
+    assert d["logits"] == 42 and d["logits"] == 42 and len(calls) == 1
+    e = LazyOutputDict()
+    e.set_lazy("x", lambda: 7)
+    assert dict(e.items()) == {"x": 7} and e.get("y", 3) == 3
+    e["x"] = 8
+    assert e["x"] == 8

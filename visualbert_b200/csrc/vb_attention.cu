@@ -229,14 +229,14 @@ attn_fwd_kernel(const AttnParams p) {
             mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
             mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
             const float mn = fmaxf(m[r], mx[r]);
-            alpha[r] = exp2f(m[r] - mn);
+            alpha[r] = fast_ex2(m[r] - mn);
             m[r] = mn;
         }
         float rs[2] = {0.f, 0.f};
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
-            s[nt][0] = exp2f(s[nt][0] - m[0]); s[nt][1] = exp2f(s[nt][1] - m[0]);
-            s[nt][2] = exp2f(s[nt][2] - m[1]); s[nt][3] = exp2f(s[nt][3] - m[1]);
+            s[nt][0] = fast_ex2(s[nt][0] - m[0]); s[nt][1] = fast_ex2(s[nt][1] - m[0]);
+            s[nt][2] = fast_ex2(s[nt][2] - m[1]); s[nt][3] = fast_ex2(s[nt][3] - m[1]);
             rs[0] += s[nt][0] + s[nt][1];
             rs[1] += s[nt][2] + s[nt][3];
         }
@@ -366,8 +366,8 @@ attn_bwd_dq_kernel(const AttnParams p) {
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
             const float b0 = sbias[buf * kBlk + nt * 8 + 2 * t], b1 = sbias[buf * kBlk + nt * 8 + 2 * t + 1];
-            const float p0 = exp2f(fmaf(s[nt][0], sc2, b0) - lse0), p1 = exp2f(fmaf(s[nt][1], sc2, b1) - lse0);
-            const float p2 = exp2f(fmaf(s[nt][2], sc2, b0) - lse1), p3 = exp2f(fmaf(s[nt][3], sc2, b1) - lse1);
+            const float p0 = fast_ex2(fmaf(s[nt][0], sc2, b0) - lse0), p1 = fast_ex2(fmaf(s[nt][1], sc2, b1) - lse0);
+            const float p2 = fast_ex2(fmaf(s[nt][2], sc2, b0) - lse1), p3 = fast_ex2(fmaf(s[nt][3], sc2, b1) - lse1);
             float e0 = dp[nt][0], e1 = dp[nt][1], e2 = dp[nt][2], e3 = dp[nt][3];
             if (p.drop_scale != 0.f) {
                 const int key = kb * kBlk + nt * 8 + 2 * t;
@@ -459,8 +459,8 @@ attn_bwd_dkv_kernel(const AttnParams p) {
             const int qi = nt * 8 + 2 * t;
             const float l0 = slse[buf * kBlk + qi], l1 = slse[buf * kBlk + qi + 1];
             const float dd0 = sD[buf * kBlk + qi], dd1 = sD[buf * kBlk + qi + 1];
-            const float p0 = exp2f(fmaf(st[nt][0], sc2, bias0) - l0), p1 = exp2f(fmaf(st[nt][1], sc2, bias0) - l1);
-            const float p2 = exp2f(fmaf(st[nt][2], sc2, bias1) - l0), p3 = exp2f(fmaf(st[nt][3], sc2, bias1) - l1);
+            const float p0 = fast_ex2(fmaf(st[nt][0], sc2, bias0) - l0), p1 = fast_ex2(fmaf(st[nt][1], sc2, bias0) - l1);
+            const float p2 = fast_ex2(fmaf(st[nt][2], sc2, bias1) - l0), p3 = fast_ex2(fmaf(st[nt][3], sc2, bias1) - l1);
             float e0 = dpt[nt][0], e1 = dpt[nt][1], e2 = dpt[nt][2], e3 = dpt[nt][3];
             float w0 = p0, w1 = p1, w2 = p2, w3 = p3;  // dropped probabilities feeding dV
             if (p.drop_scale != 0.f) {

@@ -77,28 +77,44 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
     return __bfloat1622float2(h);
 }
 
-// erf via Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7): one ex2 + one rcp + 5 FMAs.
+// raw SFU approximations (1 MUFU each, no range fix-up branches); ex2(-inf) = +0
+__device__ __forceinline__ float fast_ex2(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // gelu(x) = x * 0.5 * (1 + erf(x / sqrt(2)))   — reference modeling.py:56-61 (exact-erf form).
-__device__ __forceinline__ float erf_as(float x, float exp_neg_x2) {
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7 + SFU approximation error ~1e-6, far below the
+// bf16 output rounding): erf(|z|) = 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1 / (1 + p |z|).
+// Returns q = poly(t) * t * exp(-x^2/2) so that erf(|x|/sqrt2) = 1 - q; also hands back exp(-x^2/2).
+__device__ __forceinline__ float erfc_abs_sqrt2(float x, float& e) {
     const float ax = fabsf(x);
-    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+    e = fast_ex2(x * x * -0.72134752044448170f);              // exp(-x^2/2)
+    const float t = fast_rcp(fmaf(0.23164189f, ax, 1.0f));    // p/sqrt(2) = 0.3275911 * 0.70710678
     float poly = fmaf(1.061405429f, t, -1.453152027f);
     poly = fmaf(poly, t, 1.421413741f);
     poly = fmaf(poly, t, -0.284496736f);
     poly = fmaf(poly, t, 0.254829592f);
-    const float r = 1.0f - poly * t * exp_neg_x2;
-    return copysignf(r, x);
+    return poly * t * e;
 }
 __device__ __forceinline__ float gelu_fwd(float x) {
-    const float z = x * 0.70710678118654752f;
-    const float e = __expf(-z * z);
-    return 0.5f * x * (1.0f + erf_as(z, e));
+    float e;
+    const float q = erfc_abs_sqrt2(x, e);
+    const float hx = 0.5f * x, ha = fabsf(hx);
+    return fmaf(-ha, q, hx + ha);  // 0.5 x + 0.5 |x| (1 - q)
 }
 // d/dx gelu(x) = 0.5 (1 + erf(x/√2)) + x φ(x),  φ(x) = exp(-x²/2)/√(2π)
 __device__ __forceinline__ float gelu_bwd(float x) {
-    const float z = x * 0.70710678118654752f;
-    const float e = __expf(-z * z);
-    return 0.5f * (1.0f + erf_as(z, e)) + x * e * 0.3989422804014327f;
+    float e;
+    const float q = erfc_abs_sqrt2(x, e);
+    const float cdf = 0.5f + copysignf(fmaf(-0.5f, q, 0.5f), x);
+    return fmaf(x * e, 0.3989422804014327f, cdf);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -426,6 +426,51 @@ class BertVisualModel(PreTrainedBertModel):
         return encoded_layers, pooled_output
 
 
+class LazyOutputDict(dict):
+    """Output dict whose expensive entries are computed on first access.
+
+    The reference materialises MLM `logits` for all B*S positions ([B, S, vocab] — 5.1 GB in fp32 at the benchmark
+    config) although the loss ignores every position whose label is -1 (all visual and ~85 % of text positions,
+    M.py:1422, 1472) and its own training wrapper never reads `logits` in pretraining mode
+    (visualbert/models/model.py:290-299). Here the loss is computed from the labelled rows only — the same value
+    and gradients — and `logits` (full shape, reference semantics) is produced when somebody asks for it."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self._lazy = {}
+
+    def set_lazy(self, key, thunk):
+        self._lazy[key] = thunk
+        super().__setitem__(key, None)
+
+    def _resolve(self, key):
+        if key in self._lazy:
+            super().__setitem__(key, self._lazy.pop(key)())
+
+    def __getitem__(self, key):
+        self._resolve(key)
+        return super().__getitem__(key)
+
+    def get(self, key, default=None):
+        if key in self:
+            return self[key]
+        return default
+
+    def __setitem__(self, key, value):
+        self._lazy.pop(key, None)
+        super().__setitem__(key, value)
+
+    def items(self):
+        for k in list(self._lazy):
+            self._resolve(k)
+        return super().items()
+
+    def values(self):
+        for k in list(self._lazy):
+            self._resolve(k)
+        return super().values()
+
+
 def transform_to_batch_sequence(tensor):
     if tensor is None or tensor.dim() == 2:
         return tensor
@@ -501,6 +546,15 @@ class TrainVisualBERTObjective(PreTrainedBertModel):
             self.flickr_attention = FlickrAttention(config)
         self.apply(self.init_bert_weights)
 
+    def _masked_lm_loss(self, sequence_output, flat_labels):
+        """CrossEntropyLoss(ignore_index=-1) of the MLM head (M.py:1471-1473) evaluated on the labelled rows only:
+        ignored rows contribute neither to the sum nor to the count, so value and gradients are unchanged."""
+        labels = flat_labels.contiguous().view(-1)
+        rows = torch.nonzero(labels != -1).squeeze(1)
+        hidden = sequence_output.reshape(-1, sequence_output.size(-1)).index_select(0, rows)
+        scores = self.cls.predictions(hidden)
+        return F.cross_entropy(scores.float(), labels.index_select(0, rows))
+
     def forward(self, input_ids, token_type_ids, input_mask, visual_embeddings, position_embeddings_visual, image_mask,
                 image_text_alignment=None, confidence=None, visual_embeddings_type=None, label=None,
                 flickr_position=None, masked_lm_labels=None, image_lm_lables=None, is_random_next=None,
@@ -547,13 +601,13 @@ class TrainVisualBERTObjective(PreTrainedBertModel):
 
         head = self.training_head_type
         if head == "pretraining":
-            prediction_scores, seq_relationship_score = self.cls(sequence_output, pooled_output)
-            output_dict["logits"] = prediction_scores
+            output_dict = LazyOutputDict()
+            seq_relationship_score = _lin(pooled_output, self.cls.seq_relationship)
+            output_dict.set_lazy("logits", lambda: self.cls.predictions(sequence_output))
             output_dict["seq_relationship_score"] = seq_relationship_score
             output_dict["loss"] = None
             if flat_masked_lm_labels is not None:
-                masked_lm_loss = F.cross_entropy(prediction_scores.view(-1, self.config.vocab_size).float(),
-                                                 flat_masked_lm_labels.contiguous().view(-1), ignore_index=-1)
+                masked_lm_loss = self._masked_lm_loss(sequence_output, flat_masked_lm_labels)
                 output_dict["masked_lm_loss"] = masked_lm_loss
                 output_dict["loss"] = masked_lm_loss
                 if is_random_next is not None:
