@@ -75,7 +75,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def mark(self):
+        """Start of the timed window: earlier samples (nvidia-smi spin-up during warm-up) are dropped."""
+        self.t0 = time.time()
 
     def __exit__(self, *a):
         if self.proc is not None:
@@ -87,7 +91,10 @@ class ClockSampler:
 
     def summary(self):
         sm, mx, reasons = [], 0, set()
-        for r in self.rows:
+        t0 = getattr(self, "t0", 0.0)
+        for t, r in self.rows:
+            if t < t0:
+                continue
             try:
                 sm.append(float(r[0])); mx = max(mx, float(r[1]))
             except Exception:
@@ -221,14 +228,15 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
-    for _ in range(max(args.warmup, 3)):
-        step(resident)
-    barrier()
-    # ---- timed region: inputs resident in HBM ----
-    _lib.profile_read()
-    _lib.profile_enable(True)
-    n0 = _lib.launch_count()
-    with ClockSampler(local) as clk:
+    with ClockSampler(local) as clk:  # nvidia-smi needs ~0.5 s to start streaming: launch it before the warm-up
+        for _ in range(max(args.warmup, 3)):
+            step(resident)
+        barrier()
+        # ---- timed region: inputs resident in HBM ----
+        _lib.profile_read()
+        _lib.profile_enable(True)
+        n0 = _lib.launch_count()
+        clk.mark()
         ms_total = timed(lambda: step(resident), args.steps)
     launches = _lib.launch_count() - n0
     prof = _lib.profile_read()

@@ -64,12 +64,18 @@ def test_forward_backward_parity(name):
     # (a) reference goldens
     assert abs(loss.item() - float(gold["loss"])) <= LOSS_RTOL * abs(float(gold["loss"]))
     assert _relmax(golden_util.subsample(out["logits"].float()), gold["logits_sub"]) < ACT_TOL
-    if "nsp" in gold:
-        assert _relmax(out["seq_relationship_score"].detach().float().cpu().numpy(), gold["nsp"]) < ACT_TOL
-    # (b) oracle on the same device, fp32
+    # (b) oracle on the same device, fp32 — and the same arithmetic in torch bf16 as the noise floor
     sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     kw = {k: v for k, v in batch.items() if k != "position_embeddings_visual"}
     ref = vb_oracle.objective(sdo, cfg, c["head"], **kw)
+    sdb = {k: v.bfloat16().clone().requires_grad_(True) for k, v in sd.items()}
+    kwb = {k: (v.bfloat16() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in kw.items()}
+    refb = vb_oracle.objective(sdb, cfg, c["head"], **kwb)
+    if "nsp" in gold:
+        # W.pooled + b can cancel to ~1e-3 (tiny models): accept bf16-level error of the reference arithmetic itself
+        nsp = out["seq_relationship_score"].detach().float().cpu().numpy()
+        nsp_b = refb["seq_relationship_score"].detach().float().cpu().numpy()
+        assert _relmax(nsp, gold["nsp"]) < ACT_TOL or np.abs(nsp - gold["nsp"]).max() <= np.abs(nsp_b - gold["nsp"]).max()
     assert abs(loss.item() - ref["loss"].item()) <= LOSS_RTOL * abs(ref["loss"].item())
     assert _relmax(out["logits"].detach().float().cpu().numpy().reshape(-1), ref["logits"].detach().cpu().numpy().reshape(-1)) < ACT_TOL
     enc = model(**{**batch, "output_all_encoded_layers": True})
@@ -81,9 +87,7 @@ def test_forward_backward_parity(name):
     # gradients
     loss.backward()
     ref["loss"].backward()
-    sdb = {k: v.bfloat16().clone().requires_grad_(True) for k, v in sd.items()}  # noise floor: same math, torch bf16
-    kwb = {k: (v.bfloat16() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in kw.items()}
-    vb_oracle.objective(sdb, cfg, c["head"], **kwb)["loss"].float().backward()
+    refb["loss"].float().backward()
     gold_norms = dict(zip(gold["grad_names"].tolist(), gold["grad_norms"].tolist()))
     big = max(gold_norms.values())
     checked = 0
