@@ -15,6 +15,8 @@
 //
 // Tensor-core path here is warp-level mma.sync (m16n8k16, bf16 -> fp32); the tcgen05 budget of the
 // layer is spent in vb_gemm.cu where > 96 % of the FLOPs are.
+#include <stdlib.h>
+
 #include "../../include/vbert_b200.h"
 #include "vb_common.cuh"
 
@@ -92,34 +94,69 @@ __device__ __forceinline__ void load_afrag(uint32_t (&a)[4][4], uint32_t tile, i
         ldsm_x4(tile + swz(row, chunk), a[ks][0], a[ks][1], a[ks][2], a[ks][3]);
     }
 }
-// acc(16 x 64 n) += A(16 x 64 k) * T^T, T = tile [n=64][k=64] row-major
-__device__ __forceinline__ void gemm_nt(float (&acc)[8][4], const uint32_t (&a)[4][4], uint32_t tile, int lane) {
+// acc(16 x 64 n) += A(16 x 64 k) * T^T, T = tile [n=64][k=64] row-major; only the first `nvalid`
+// rows of T (n index) carry data — whole 16-wide n pairs beyond it are skipped (warp-uniform).
+__device__ __forceinline__ void gemm_nt(float (&acc)[8][4], const uint32_t (&a)[4][4], uint32_t tile, int lane,
+                                        int nvalid = 64) {
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
+    for (int np = 0; np < 4; ++np) {
+        if (np * 16 < nvalid) {
 #pragma unroll
-        for (int np = 0; np < 4; ++np) {
-            const int row = np * 16 + (lane & 7) + (lane >> 4) * 8;
-            const int chunk = ks * 2 + ((lane >> 3) & 1);
-            uint32_t b0, b1, b2, b3;
-            ldsm_x4(tile + swz(row, chunk), b0, b1, b2, b3);
-            mma16816(acc[2 * np], a[ks], b0, b1);
-            mma16816(acc[2 * np + 1], a[ks], b2, b3);
+            for (int ks = 0; ks < 4; ++ks) {
+                const int row = np * 16 + (lane & 7) + (lane >> 4) * 8;
+                const int chunk = ks * 2 + ((lane >> 3) & 1);
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4(tile + swz(row, chunk), b0, b1, b2, b3);
+                mma16816(acc[2 * np], a[ks], b0, b1);
+                mma16816(acc[2 * np + 1], a[ks], b2, b3);
+            }
         }
     }
 }
-// acc(16 x 64 n) += A(16 x 64 k) * T, T = tile [k=64][n=64] row-major
-__device__ __forceinline__ void gemm_nn(float (&acc)[8][4], const uint32_t (&a)[4][4], uint32_t tile, int lane) {
+// acc(16 x 64 n) += A(16 x 64 k) * T, T = tile [k=64][n=64] row-major; k-steps beyond `kvalid` rows
+// of T are skipped (their A columns are exact zeros).
+__device__ __forceinline__ void gemm_nn(float (&acc)[8][4], const uint32_t (&a)[4][4], uint32_t tile, int lane,
+                                        int kvalid = 64) {
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
+        if (ks * 16 < kvalid) {
 #pragma unroll
-        for (int np = 0; np < 4; ++np) {
-            const int row = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-            const int chunk = np * 2 + (lane >> 4);
-            uint32_t b0, b1, b2, b3;
-            ldsm_x4_t(tile + swz(row, chunk), b0, b1, b2, b3);
-            mma16816(acc[2 * np], a[ks], b0, b1);
-            mma16816(acc[2 * np + 1], a[ks], b2, b3);
+            for (int np = 0; np < 4; ++np) {
+                const int row = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                const int chunk = np * 2 + (lane >> 4);
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4_t(tile + swz(row, chunk), b0, b1, b2, b3);
+                mma16816(acc[2 * np], a[ks], b0, b1);
+                mma16816(acc[2 * np + 1], a[ks], b2, b3);
+            }
         }
+    }
+}
+// half-width variant: acc(16 x 32) = A * T^T for n in [32*half, 32*half + 32)
+__device__ __forceinline__ void gemm_nt_half(float (&acc)[4][4], const uint32_t (&a)[4][4], uint32_t tile, int lane,
+                                             int half, int nvalid) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int np = half * 2 + q;
+        if (np * 16 < nvalid) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const int row = np * 16 + (lane & 7) + (lane >> 4) * 8;
+                const int chunk = ks * 2 + ((lane >> 3) & 1);
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4(tile + swz(row, chunk), b0, b1, b2, b3);
+                mma16816(acc[2 * q], a[ks], b0, b1);
+                mma16816(acc[2 * q + 1], a[ks], b2, b3);
+            }
+        }
+    }
+}
+__device__ __forceinline__ void cp_async_wait_dyn(int pending) {  // allow `pending` newest groups in flight
+    switch (pending) {
+        case 0: cp_async_wait<0>(); break;
+        case 1: cp_async_wait<1>(); break;
+        case 2: cp_async_wait<2>(); break;
+        default: cp_async_wait<3>(); break;
     }
 }
 // accumulator tile (16 x 64, fp32) -> A fragments (bf16) for the next GEMM
@@ -166,10 +203,16 @@ __device__ __forceinline__ void store_acc(bf16* base, long long ld, int row0, in
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-attn_fwd_kernel(const AttnParams p) {
-    __shared__ __align__(128) uint8_t smem[5 * kTileBytes];
-    __shared__ float sbias[kBlk * 2];
+// Shared memory: Q tile | K tiles [kMaxSub] | V tiles [kMaxSub]. A "stage" holds up to kMaxSub * 64
+// keys; for S <= 256 (every reference config) the whole K/V of the head is resident, all cp.async are
+// issued up-front (one commit group per 64-key sub-block) and the warps only wait for the group they
+// are about to consume.
+constexpr int kMaxSub = 4;
+
+__global__ void __launch_bounds__(128, 3)
+attn_fwd_kernel(const AttnParams p, const int nsub) {
+    extern __shared__ __align__(128) uint8_t dsmem[];
+    __shared__ float sbias[kMaxSub * kBlk];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -178,13 +221,8 @@ attn_fwd_kernel(const AttnParams p) {
     const bf16* qbase = p.qkv + static_cast<long long>(b) * S * ld + h * kHd;
     const bf16* kbase = qbase + p.H;
     const bf16* vbase = qbase + 2 * p.H;
-    const uint32_t sQ = smem_u32(smem), sK0 = sQ + kTileBytes, sV0 = sQ + 3 * kTileBytes;
+    const uint32_t sQ = smem_u32(dsmem), sK0 = sQ + kTileBytes, sV0 = sK0 + nsub * kTileBytes;
     const int nkb = (S + kBlk - 1) / kBlk;
-
-    load_tile(sQ, qbase, ld, qb * kBlk, S, tid);
-    load_tile(sK0, kbase, ld, 0, S, tid);
-    load_tile(sV0, vbase, ld, 0, S, tid);
-    cp_async_commit();
 
     const float sc2 = p.scale * kLog2e;
     float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
@@ -193,80 +231,85 @@ attn_fwd_kernel(const AttnParams p) {
     uint32_t qf[4][4];
     const unsigned bh = static_cast<unsigned>(b * p.A + h);
     const int qrow0 = qb * kBlk + warp * 16;
+    const bool active = qrow0 < S;  // warps whose 16 query rows are all padding only help with the loads
 
-    for (int kb = 0; kb < nkb; ++kb) {
-        const int buf = kb & 1;
-        if (tid < kBlk) {
-            const int key = kb * kBlk + tid;
-            sbias[buf * kBlk + tid] = key < S ? p.mask_bias[static_cast<long long>(b) * S + key] * kLog2e : -INFINITY;
-        }
-        if (kb + 1 < nkb) {
-            load_tile(sK0 + (buf ^ 1) * kTileBytes, kbase, ld, (kb + 1) * kBlk, S, tid);
-            load_tile(sV0 + (buf ^ 1) * kTileBytes, vbase, ld, (kb + 1) * kBlk, S, tid);
+    for (int kb0 = 0; kb0 < nkb; kb0 += nsub) {
+        const int nb = min(nsub, nkb - kb0);
+        if (kb0 > 0) __syncthreads();  // previous stage fully consumed
+        if (kb0 == 0) load_tile(sQ, qbase, ld, qb * kBlk, S, tid);
+        for (int j = 0; j < nb; ++j) {
+            load_tile(sK0 + j * kTileBytes, kbase, ld, (kb0 + j) * kBlk, S, tid);
+            load_tile(sV0 + j * kTileBytes, vbase, ld, (kb0 + j) * kBlk, S, tid);
             cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
         }
-        __syncthreads();
-        if (kb == 0) load_afrag(qf, sQ, warp * 16, lane);
-
-        float s[8][4];
-        zero_acc(s);
-        gemm_nt(s, qf, sK0 + buf * kTileBytes, lane);
-        float mx[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            const float b0 = sbias[buf * kBlk + nt * 8 + 2 * t], b1 = sbias[buf * kBlk + nt * 8 + 2 * t + 1];
-            s[nt][0] = fmaf(s[nt][0], sc2, b0); s[nt][1] = fmaf(s[nt][1], sc2, b1);
-            s[nt][2] = fmaf(s[nt][2], sc2, b0); s[nt][3] = fmaf(s[nt][3], sc2, b1);
-            mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
-            mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+        for (int i = tid; i < nb * kBlk; i += 128) {
+            const int key = kb0 * kBlk + i;
+            sbias[i] = key < S ? p.mask_bias[static_cast<long long>(b) * S + key] * kLog2e : -INFINITY;
         }
-        float alpha[2];
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
-            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-            const float mn = fmaxf(m[r], mx[r]);
-            alpha[r] = fast_ex2(m[r] - mn);
-            m[r] = mn;
-        }
-        float rs[2] = {0.f, 0.f};
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            s[nt][0] = fast_ex2(s[nt][0] - m[0]); s[nt][1] = fast_ex2(s[nt][1] - m[0]);
-            s[nt][2] = fast_ex2(s[nt][2] - m[1]); s[nt][3] = fast_ex2(s[nt][3] - m[1]);
-            rs[0] += s[nt][0] + s[nt][1];
-            rs[1] += s[nt][2] + s[nt][3];
-        }
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
-            rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
-            l[r] = l[r] * alpha[r] + rs[r];
-        }
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            o[nt][0] *= alpha[0]; o[nt][1] *= alpha[0];
-            o[nt][2] *= alpha[1]; o[nt][3] *= alpha[1];
-        }
-        if (p.drop_scale != 0.f) {
+        for (int j = 0; j < nb; ++j) {
+            cp_async_wait_dyn(nb - 1 - j);
+            __syncthreads();
+            if (!active) continue;
+            if (kb0 == 0 && j == 0) load_afrag(qf, sQ, warp * 16, lane);
+            const int kb = kb0 + j;
+            const int kvalid = min(kBlk, S - kb * kBlk);
+            float s[8][4];
+            zero_acc(s);
+            gemm_nt(s, qf, sK0 + j * kTileBytes, lane, kvalid);
+            float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt) {
-                const int key = kb * kBlk + nt * 8 + 2 * t;
-                const int qa = qrow0 + g, qc = qrow0 + g + 8;
-                s[nt][0] = attn_keep(p.drop_seed, bh, qa, key, S, p.drop_thresh16) ? s[nt][0] * p.drop_scale : 0.f;
-                s[nt][1] = attn_keep(p.drop_seed, bh, qa, key + 1, S, p.drop_thresh16) ? s[nt][1] * p.drop_scale : 0.f;
-                s[nt][2] = attn_keep(p.drop_seed, bh, qc, key, S, p.drop_thresh16) ? s[nt][2] * p.drop_scale : 0.f;
-                s[nt][3] = attn_keep(p.drop_seed, bh, qc, key + 1, S, p.drop_thresh16) ? s[nt][3] * p.drop_scale : 0.f;
+                const float b0 = sbias[j * kBlk + nt * 8 + 2 * t], b1 = sbias[j * kBlk + nt * 8 + 2 * t + 1];
+                s[nt][0] = fmaf(s[nt][0], sc2, b0); s[nt][1] = fmaf(s[nt][1], sc2, b1);
+                s[nt][2] = fmaf(s[nt][2], sc2, b0); s[nt][3] = fmaf(s[nt][3], sc2, b1);
+                mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+                mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
             }
+            float alpha[2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+                mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+                const float mn = fmaxf(m[r], mx[r]);
+                alpha[r] = fast_ex2(m[r] - mn);
+                m[r] = mn;
+            }
+            float rs[2] = {0.f, 0.f};
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                s[nt][0] = fast_ex2(s[nt][0] - m[0]); s[nt][1] = fast_ex2(s[nt][1] - m[0]);
+                s[nt][2] = fast_ex2(s[nt][2] - m[1]); s[nt][3] = fast_ex2(s[nt][3] - m[1]);
+                rs[0] += s[nt][0] + s[nt][1];
+                rs[1] += s[nt][2] + s[nt][3];
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
+                rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
+                l[r] = l[r] * alpha[r] + rs[r];
+            }
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                o[nt][0] *= alpha[0]; o[nt][1] *= alpha[0];
+                o[nt][2] *= alpha[1]; o[nt][3] *= alpha[1];
+            }
+            if (p.drop_scale != 0.f) {
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    const int key = kb * kBlk + nt * 8 + 2 * t;
+                    const int qa = qrow0 + g, qc = qrow0 + g + 8;
+                    s[nt][0] = attn_keep(p.drop_seed, bh, qa, key, S, p.drop_thresh16) ? s[nt][0] * p.drop_scale : 0.f;
+                    s[nt][1] = attn_keep(p.drop_seed, bh, qa, key + 1, S, p.drop_thresh16) ? s[nt][1] * p.drop_scale : 0.f;
+                    s[nt][2] = attn_keep(p.drop_seed, bh, qc, key, S, p.drop_thresh16) ? s[nt][2] * p.drop_scale : 0.f;
+                    s[nt][3] = attn_keep(p.drop_seed, bh, qc, key + 1, S, p.drop_thresh16) ? s[nt][3] * p.drop_scale : 0.f;
+                }
+            }
+            uint32_t pf[4][4];
+            acc_to_afrag(pf, s);
+            gemm_nn(o, pf, sV0 + j * kTileBytes, lane, kvalid);
         }
-        uint32_t pf[4][4];
-        acc_to_afrag(pf, s);
-        gemm_nn(o, pf, sV0 + buf * kTileBytes, lane);
-        __syncthreads();  // all warps done with this K/V buffer before it is refilled
     }
+    if (!active) return;
     const float inv0 = 1.f / l[0], inv1 = 1.f / l[1];
     store_acc(p.ctx + static_cast<long long>(b) * S * p.H + h * kHd, p.H, qrow0, S, o, lane, inv0, inv1);
     if (t == 0 && p.lse != nullptr) {
@@ -278,11 +321,13 @@ attn_fwd_kernel(const AttnParams p) {
 
 // ------------------------------------------------------------------------------------------------
 // backward A: per query block — D = rowsum(dO * O), dQ = scale * sum_k dS K
+// Shared memory: Q | dO | O | K tiles [nsub] | V tiles [nsub]
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-attn_bwd_dq_kernel(const AttnParams p) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
+attn_bwd_dq_kernel(const AttnParams p, const int nsub) {
     extern __shared__ __align__(128) uint8_t dsmem[];
-    __shared__ float sbias[kBlk * 2];
+    __shared__ float sbias[kMaxSub * kBlk];
     __shared__ float sD[kBlk];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -294,108 +339,122 @@ attn_bwd_dq_kernel(const AttnParams p) {
     const bf16* vbase = qbase + 2 * p.H;
     const bf16* obase = p.ctx + static_cast<long long>(b) * S * p.H + h * kHd;
     const bf16* dobase = p.dctx + static_cast<long long>(b) * S * p.H + h * kHd;
-    // tiles: Q, dO, O, K[2], V[2]
     const uint32_t sQ = smem_u32(dsmem), sdO = sQ + kTileBytes, sO = sQ + 2 * kTileBytes;
-    const uint32_t sK0 = sQ + 3 * kTileBytes, sV0 = sQ + 5 * kTileBytes;
+    const uint32_t sK0 = sQ + 3 * kTileBytes, sV0 = sK0 + nsub * kTileBytes;
     const int nkb = (S + kBlk - 1) / kBlk;
-
-    load_tile(sQ, qbase, ld, qb * kBlk, S, tid);
-    load_tile(sdO, dobase, p.H, qb * kBlk, S, tid);
-    load_tile(sO, obase, p.H, qb * kBlk, S, tid);
-    load_tile(sK0, kbase, ld, 0, S, tid);
-    load_tile(sV0, vbase, ld, 0, S, tid);
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
-    {   // D[row] = sum_d dO * O : two threads per row
-        const int r = tid >> 1, half = tid & 1;
-        float acc = 0.f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int chunk = half * 4 + c;
-            const uint4 a = *reinterpret_cast<const uint4*>(dsmem + kTileBytes + swz(r, chunk));
-            const uint4 o = *reinterpret_cast<const uint4*>(dsmem + 2 * kTileBytes + swz(r, chunk));
-            const uint32_t av[4] = {a.x, a.y, a.z, a.w}, ov[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 x = unpack_bf16x2(av[i]), y = unpack_bf16x2(ov[i]);
-                acc += x.x * y.x + x.y * y.y;
-            }
-        }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        if (half == 0) {
-            sD[r] = acc;
-            const int q = qb * kBlk + r;
-            if (q < S) p.drow[(static_cast<long long>(b) * p.A + h) * S + q] = acc;
-        }
-    }
-    uint32_t qf[4][4], dof[4][4];
-    load_afrag(qf, sQ, warp * 16, lane);
-    load_afrag(dof, sdO, warp * 16, lane);
     const int qrow0 = qb * kBlk + warp * 16;
+    const bool active = qrow0 < S;
     const float* lsep = p.lse + (static_cast<long long>(b) * p.A + h) * S;
     const float lse0 = (qrow0 + g < S) ? lsep[qrow0 + g] * kLog2e : 0.f;
     const float lse1 = (qrow0 + g + 8 < S) ? lsep[qrow0 + g + 8] * kLog2e : 0.f;
-    __syncthreads();
-    const float d0 = sD[warp * 16 + g], d1 = sD[warp * 16 + g + 8];
     const float sc2 = p.scale * kLog2e;
     const unsigned bh = static_cast<unsigned>(b * p.A + h);
+    uint32_t qf[4][4], dof[4][4];
+    float d0 = 0.f, d1 = 0.f;
     float dq[8][4];
     zero_acc(dq);
 
-    for (int kb = 0; kb < nkb; ++kb) {
-        const int buf = kb & 1;
-        if (tid < kBlk) {
-            const int key = kb * kBlk + tid;
-            sbias[buf * kBlk + tid] = key < S ? p.mask_bias[static_cast<long long>(b) * S + key] * kLog2e : -INFINITY;
+    for (int kb0 = 0; kb0 < nkb; kb0 += nsub) {
+        const int nb = min(nsub, nkb - kb0);
+        if (kb0 > 0) __syncthreads();
+        if (kb0 == 0) {
+            load_tile(sQ, qbase, ld, qb * kBlk, S, tid);
+            load_tile(sdO, dobase, p.H, qb * kBlk, S, tid);
+            load_tile(sO, obase, p.H, qb * kBlk, S, tid);
         }
-        if (kb + 1 < nkb) {
-            load_tile(sK0 + (buf ^ 1) * kTileBytes, kbase, ld, (kb + 1) * kBlk, S, tid);
-            load_tile(sV0 + (buf ^ 1) * kTileBytes, vbase, ld, (kb + 1) * kBlk, S, tid);
+        for (int j = 0; j < nb; ++j) {
+            load_tile(sK0 + j * kTileBytes, kbase, ld, (kb0 + j) * kBlk, S, tid);
+            load_tile(sV0 + j * kTileBytes, vbase, ld, (kb0 + j) * kBlk, S, tid);
             cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
         }
-        __syncthreads();
-        float s[8][4], dp[8][4];
-        zero_acc(s);
-        zero_acc(dp);
-        gemm_nt(s, qf, sK0 + buf * kTileBytes, lane);
-        gemm_nt(dp, dof, sV0 + buf * kTileBytes, lane);
+        for (int i = tid; i < nb * kBlk; i += 128) {
+            const int key = kb0 * kBlk + i;
+            sbias[i] = key < S ? p.mask_bias[static_cast<long long>(b) * S + key] * kLog2e : -INFINITY;
+        }
+        for (int j = 0; j < nb; ++j) {
+            cp_async_wait_dyn(nb - 1 - j);
+            __syncthreads();
+            if (kb0 == 0 && j == 0) {
+                // D[row] = sum_d dO * O : two threads per row (block-wide, then one more barrier)
+                const int r = tid >> 1, half = tid & 1;
+                float acc = 0.f;
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            const float b0 = sbias[buf * kBlk + nt * 8 + 2 * t], b1 = sbias[buf * kBlk + nt * 8 + 2 * t + 1];
-            const float p0 = fast_ex2(fmaf(s[nt][0], sc2, b0) - lse0), p1 = fast_ex2(fmaf(s[nt][1], sc2, b1) - lse0);
-            const float p2 = fast_ex2(fmaf(s[nt][2], sc2, b0) - lse1), p3 = fast_ex2(fmaf(s[nt][3], sc2, b1) - lse1);
-            float e0 = dp[nt][0], e1 = dp[nt][1], e2 = dp[nt][2], e3 = dp[nt][3];
-            if (p.drop_scale != 0.f) {
-                const int key = kb * kBlk + nt * 8 + 2 * t;
-                const int qa = qrow0 + g, qc = qrow0 + g + 8;
-                e0 = attn_keep(p.drop_seed, bh, qa, key, S, p.drop_thresh16) ? e0 * p.drop_scale : 0.f;
-                e1 = attn_keep(p.drop_seed, bh, qa, key + 1, S, p.drop_thresh16) ? e1 * p.drop_scale : 0.f;
-                e2 = attn_keep(p.drop_seed, bh, qc, key, S, p.drop_thresh16) ? e2 * p.drop_scale : 0.f;
-                e3 = attn_keep(p.drop_seed, bh, qc, key + 1, S, p.drop_thresh16) ? e3 * p.drop_scale : 0.f;
+                for (int c = 0; c < 4; ++c) {
+                    const int chunk = half * 4 + c;
+                    const uint4 a = *reinterpret_cast<const uint4*>(dsmem + kTileBytes + swz(r, chunk));
+                    const uint4 ov = *reinterpret_cast<const uint4*>(dsmem + 2 * kTileBytes + swz(r, chunk));
+                    const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {ov.x, ov.y, ov.z, ov.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 x = unpack_bf16x2(av[i]), y = unpack_bf16x2(bv[i]);
+                        acc += x.x * y.x + x.y * y.y;
+                    }
+                }
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                if (half == 0) {
+                    sD[r] = acc;
+                    const int q = qb * kBlk + r;
+                    if (q < S) p.drow[(static_cast<long long>(b) * p.A + h) * S + q] = acc;
+                }
+                __syncthreads();
+                if (active) {
+                    load_afrag(qf, sQ, warp * 16, lane);
+                    load_afrag(dof, sdO, warp * 16, lane);
+                    d0 = sD[warp * 16 + g];
+                    d1 = sD[warp * 16 + g + 8];
+                }
             }
-            s[nt][0] = p0 * (e0 - d0); s[nt][1] = p1 * (e1 - d0);
-            s[nt][2] = p2 * (e2 - d1); s[nt][3] = p3 * (e3 - d1);
+            if (!active) continue;
+            const int kb = kb0 + j;
+            const int kvalid = min(kBlk, S - kb * kBlk);
+            float s[8][4];
+            zero_acc(s);
+            gemm_nt(s, qf, sK0 + j * kTileBytes, lane, kvalid);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {  // dP = dO V^T in two 32-key halves (register pressure)
+                float dp[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+                gemm_nt_half(dp, dof, sV0 + j * kTileBytes, lane, hh, kvalid);
+#pragma unroll
+                for (int n4 = 0; n4 < 4; ++n4) {
+                    const int nt = hh * 4 + n4;
+                    const float b0 = sbias[j * kBlk + nt * 8 + 2 * t], b1 = sbias[j * kBlk + nt * 8 + 2 * t + 1];
+                    const float p0 = fast_ex2(fmaf(s[nt][0], sc2, b0) - lse0), p1 = fast_ex2(fmaf(s[nt][1], sc2, b1) - lse0);
+                    const float p2 = fast_ex2(fmaf(s[nt][2], sc2, b0) - lse1), p3 = fast_ex2(fmaf(s[nt][3], sc2, b1) - lse1);
+                    float e0 = dp[n4][0], e1 = dp[n4][1], e2 = dp[n4][2], e3 = dp[n4][3];
+                    if (p.drop_scale != 0.f) {
+                        const int key = kb * kBlk + nt * 8 + 2 * t;
+                        const int qa = qrow0 + g, qc = qrow0 + g + 8;
+                        e0 = attn_keep(p.drop_seed, bh, qa, key, S, p.drop_thresh16) ? e0 * p.drop_scale : 0.f;
+                        e1 = attn_keep(p.drop_seed, bh, qa, key + 1, S, p.drop_thresh16) ? e1 * p.drop_scale : 0.f;
+                        e2 = attn_keep(p.drop_seed, bh, qc, key, S, p.drop_thresh16) ? e2 * p.drop_scale : 0.f;
+                        e3 = attn_keep(p.drop_seed, bh, qc, key + 1, S, p.drop_thresh16) ? e3 * p.drop_scale : 0.f;
+                    }
+                    s[nt][0] = p0 * (e0 - d0); s[nt][1] = p1 * (e1 - d0);
+                    s[nt][2] = p2 * (e2 - d1); s[nt][3] = p3 * (e3 - d1);
+                }
+            }
+            uint32_t dsf[4][4];
+            acc_to_afrag(dsf, s);
+            gemm_nn(dq, dsf, sK0 + j * kTileBytes, lane, kvalid);
         }
-        uint32_t dsf[4][4];
-        acc_to_afrag(dsf, s);
-        gemm_nn(dq, dsf, sK0 + buf * kTileBytes, lane);
-        __syncthreads();
     }
+    if (!active) return;
     store_acc(p.dqkv + static_cast<long long>(b) * S * ld + h * kHd, ld, qrow0, S, dq, lane, p.scale, p.scale);
 }
 
 // ------------------------------------------------------------------------------------------------
 // backward B: per key block — dV = P_drop^T dO, dK = scale * dS^T Q
+// Shared memory: K | V | Q tiles [nsub] | dO tiles [nsub]; K/V fragments are re-read from shared memory
+// per query block instead of being pinned in 32 registers.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-attn_bwd_dkv_kernel(const AttnParams p) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
+attn_bwd_dkv_kernel(const AttnParams p, const int nsub) {
     extern __shared__ __align__(128) uint8_t dsmem[];
-    __shared__ float slse[kBlk * 2];
-    __shared__ float sD[kBlk * 2];
+    __shared__ float slse[kMaxSub * kBlk];
+    __shared__ float sD[kMaxSub * kBlk];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int kbk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -405,86 +464,106 @@ attn_bwd_dkv_kernel(const AttnParams p) {
     const bf16* kbase = qbase + p.H;
     const bf16* vbase = qbase + 2 * p.H;
     const bf16* dobase = p.dctx + static_cast<long long>(b) * S * p.H + h * kHd;
-    // tiles: K, V, Q[2], dO[2]
-    const uint32_t sK = smem_u32(dsmem), sV = sK + kTileBytes, sQ0 = sK + 2 * kTileBytes, sdO0 = sK + 4 * kTileBytes;
+    const uint32_t sK = smem_u32(dsmem), sV = sK + kTileBytes, sQ0 = sK + 2 * kTileBytes, sdO0 = sQ0 + nsub * kTileBytes;
     const int nqb = (S + kBlk - 1) / kBlk;
     const float* lsep = p.lse + (static_cast<long long>(b) * p.A + h) * S;
     const float* drp = p.drow + (static_cast<long long>(b) * p.A + h) * S;
-
-    load_tile(sK, kbase, ld, kbk * kBlk, S, tid);
-    load_tile(sV, vbase, ld, kbk * kBlk, S, tid);
-    load_tile(sQ0, qbase, ld, 0, S, tid);
-    load_tile(sdO0, dobase, p.H, 0, S, tid);
-    cp_async_commit();
-
     const int krow0 = kbk * kBlk + warp * 16;
+    const bool active = krow0 < S;
     const int ka = krow0 + g, kc = krow0 + g + 8;
     const float bias0 = ka < S ? p.mask_bias[static_cast<long long>(b) * S + ka] * kLog2e : -INFINITY;
     const float bias1 = kc < S ? p.mask_bias[static_cast<long long>(b) * S + kc] * kLog2e : -INFINITY;
     const float sc2 = p.scale * kLog2e;
     const unsigned bh = static_cast<unsigned>(b * p.A + h);
-    uint32_t kf[4][4], vf[4][4];
     float dk[8][4], dv[8][4];
     zero_acc(dk);
     zero_acc(dv);
 
-    for (int qb = 0; qb < nqb; ++qb) {
-        const int buf = qb & 1;
-        if (tid < kBlk) {
-            const int q = qb * kBlk + tid;
-            slse[buf * kBlk + tid] = q < S ? lsep[q] * kLog2e : INFINITY;  // +inf => p = 0 for padded queries
-            sD[buf * kBlk + tid] = q < S ? drp[q] : 0.f;
+    for (int qb0 = 0; qb0 < nqb; qb0 += nsub) {
+        const int nb = min(nsub, nqb - qb0);
+        if (qb0 > 0) __syncthreads();
+        if (qb0 == 0) {
+            load_tile(sK, kbase, ld, kbk * kBlk, S, tid);
+            load_tile(sV, vbase, ld, kbk * kBlk, S, tid);
         }
-        if (qb + 1 < nqb) {
-            load_tile(sQ0 + (buf ^ 1) * kTileBytes, qbase, ld, (qb + 1) * kBlk, S, tid);
-            load_tile(sdO0 + (buf ^ 1) * kTileBytes, dobase, p.H, (qb + 1) * kBlk, S, tid);
+        for (int j = 0; j < nb; ++j) {
+            load_tile(sQ0 + j * kTileBytes, qbase, ld, (qb0 + j) * kBlk, S, tid);
+            load_tile(sdO0 + j * kTileBytes, dobase, p.H, (qb0 + j) * kBlk, S, tid);
             cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
         }
-        __syncthreads();
-        if (qb == 0) {
-            load_afrag(kf, sK, warp * 16, lane);
-            load_afrag(vf, sV, warp * 16, lane);
+        for (int i = tid; i < nb * kBlk; i += 128) {
+            const int q = qb0 * kBlk + i;
+            slse[i] = q < S ? lsep[q] * kLog2e : INFINITY;  // +inf => p = 0 for padded queries
+            sD[i] = q < S ? drp[q] : 0.f;
         }
-        float st[8][4], dpt[8][4];
-        zero_acc(st);
-        zero_acc(dpt);
-        gemm_nt(st, kf, sQ0 + buf * kTileBytes, lane);    // S^T  = K Q^T   (16 keys x 64 queries)
-        gemm_nt(dpt, vf, sdO0 + buf * kTileBytes, lane);  // dP^T = V dO^T
-        float pt[8][4];
+        for (int j = 0; j < nb; ++j) {
+            cp_async_wait_dyn(nb - 1 - j);
+            __syncthreads();
+            if (!active) continue;
+            const int qb = qb0 + j;
+            const int qvalid = min(kBlk, S - qb * kBlk);
+            uint32_t af[4][4];
+            float st[8][4];
+            zero_acc(st);
+            load_afrag(af, sK, warp * 16, lane);
+            gemm_nt(st, af, sQ0 + j * kTileBytes, lane, qvalid);  // S^T = K Q^T (16 keys x 64 queries)
+            // probabilities (st := P^T); dropped copy -> A fragments of the dV GEMM
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            const int qi = nt * 8 + 2 * t;
-            const float l0 = slse[buf * kBlk + qi], l1 = slse[buf * kBlk + qi + 1];
-            const float dd0 = sD[buf * kBlk + qi], dd1 = sD[buf * kBlk + qi + 1];
-            const float p0 = fast_ex2(fmaf(st[nt][0], sc2, bias0) - l0), p1 = fast_ex2(fmaf(st[nt][1], sc2, bias0) - l1);
-            const float p2 = fast_ex2(fmaf(st[nt][2], sc2, bias1) - l0), p3 = fast_ex2(fmaf(st[nt][3], sc2, bias1) - l1);
-            float e0 = dpt[nt][0], e1 = dpt[nt][1], e2 = dpt[nt][2], e3 = dpt[nt][3];
-            float w0 = p0, w1 = p1, w2 = p2, w3 = p3;  // dropped probabilities feeding dV
-            if (p.drop_scale != 0.f) {
-                const int q = qb * kBlk + qi;
-                const bool k0 = attn_keep(p.drop_seed, bh, q, ka, S, p.drop_thresh16);
-                const bool k1 = attn_keep(p.drop_seed, bh, q + 1, ka, S, p.drop_thresh16);
-                const bool k2 = attn_keep(p.drop_seed, bh, q, kc, S, p.drop_thresh16);
-                const bool k3 = attn_keep(p.drop_seed, bh, q + 1, kc, S, p.drop_thresh16);
-                e0 = k0 ? e0 * p.drop_scale : 0.f; w0 = k0 ? w0 * p.drop_scale : 0.f;
-                e1 = k1 ? e1 * p.drop_scale : 0.f; w1 = k1 ? w1 * p.drop_scale : 0.f;
-                e2 = k2 ? e2 * p.drop_scale : 0.f; w2 = k2 ? w2 * p.drop_scale : 0.f;
-                e3 = k3 ? e3 * p.drop_scale : 0.f; w3 = k3 ? w3 * p.drop_scale : 0.f;
+            for (int nt = 0; nt < 8; ++nt) {
+                const int qi = nt * 8 + 2 * t;
+                const float l0 = slse[j * kBlk + qi], l1 = slse[j * kBlk + qi + 1];
+                st[nt][0] = fast_ex2(fmaf(st[nt][0], sc2, bias0) - l0); st[nt][1] = fast_ex2(fmaf(st[nt][1], sc2, bias0) - l1);
+                st[nt][2] = fast_ex2(fmaf(st[nt][2], sc2, bias1) - l0); st[nt][3] = fast_ex2(fmaf(st[nt][3], sc2, bias1) - l1);
             }
-            pt[nt][0] = w0; pt[nt][1] = w1; pt[nt][2] = w2; pt[nt][3] = w3;
-            st[nt][0] = p0 * (e0 - dd0); st[nt][1] = p1 * (e1 - dd1);
-            st[nt][2] = p2 * (e2 - dd0); st[nt][3] = p3 * (e3 - dd1);
+            unsigned keepbits = 0xffffffffu;
+            if (p.drop_scale != 0.f) {
+                keepbits = 0;
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    const int q = qb * kBlk + nt * 8 + 2 * t;
+                    keepbits |= static_cast<unsigned>(attn_keep(p.drop_seed, bh, q, ka, S, p.drop_thresh16)) << (nt * 4);
+                    keepbits |= static_cast<unsigned>(attn_keep(p.drop_seed, bh, q + 1, ka, S, p.drop_thresh16)) << (nt * 4 + 1);
+                    keepbits |= static_cast<unsigned>(attn_keep(p.drop_seed, bh, q, kc, S, p.drop_thresh16)) << (nt * 4 + 2);
+                    keepbits |= static_cast<unsigned>(attn_keep(p.drop_seed, bh, q + 1, kc, S, p.drop_thresh16)) << (nt * 4 + 3);
+                }
+            }
+            const float ds = p.drop_scale != 0.f ? p.drop_scale : 1.f;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                float w[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int nt = 2 * jj + (e >> 2), c = e & 3;
+                    w[e] = ((keepbits >> (nt * 4 + c)) & 1u) ? st[nt][c] * ds : 0.f;
+                }
+                af[jj][0] = pack_bf16x2(w[0], w[1]); af[jj][1] = pack_bf16x2(w[2], w[3]);
+                af[jj][2] = pack_bf16x2(w[4], w[5]); af[jj][3] = pack_bf16x2(w[6], w[7]);
+            }
+            gemm_nn(dv, af, sdO0 + j * kTileBytes, lane, qvalid);  // dV += P_drop^T dO
+            load_afrag(af, sV, warp * 16, lane);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {  // dP^T = V dO^T in two 32-query halves (register pressure)
+                float dpt[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f;
+                gemm_nt_half(dpt, af, sdO0 + j * kTileBytes, lane, hh, qvalid);
+#pragma unroll
+                for (int n4 = 0; n4 < 4; ++n4) {
+                    const int nt = hh * 4 + n4;
+                    const int qi = nt * 8 + 2 * t;
+                    const float dd0 = sD[j * kBlk + qi], dd1 = sD[j * kBlk + qi + 1];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float e = ((keepbits >> (nt * 4 + c)) & 1u) ? dpt[n4][c] * ds : 0.f;
+                        st[nt][c] *= e - ((c & 1) ? dd1 : dd0);
+                    }
+                }
+            }
+            acc_to_afrag(af, st);
+            gemm_nn(dk, af, sQ0 + j * kTileBytes, lane, qvalid);  // dK += dS^T Q
         }
-        uint32_t af[4][4];
-        acc_to_afrag(af, pt);
-        gemm_nn(dv, af, sdO0 + buf * kTileBytes, lane);  // dV += P^T dO
-        acc_to_afrag(af, st);
-        gemm_nn(dk, af, sQ0 + buf * kTileBytes, lane);   // dK += dS^T Q
-        __syncthreads();
     }
+    if (!active) return;
     bf16* dbase = p.dqkv + static_cast<long long>(b) * S * ld + h * kHd;
     store_acc(dbase + p.H, ld, krow0, S, dk, lane, p.scale, p.scale);
     store_acc(dbase + 2 * p.H, ld, krow0, S, dv, lane, 1.f, 1.f);
@@ -525,13 +604,22 @@ int attn_fwd(const void* qkv, const float* mask_bias, void* ctx, float* lse, int
     int rc = fill_params(p, qkv, mask_bias, ctx, lse, nullptr, nullptr, nullptr, B, S, A, H, dropout_p, seed, stream_id);
     if (rc) return rc;
     dim3 grid((S + kBlk - 1) / kBlk, A, B);
+    const int nsub = static_cast<int>(grid.x) < kMaxSub ? static_cast<int>(grid.x) : kMaxSub;
+    const int smem = (1 + 2 * nsub) * kTileBytes;
+    static bool configured = false;
+    if (!configured) {
+        VB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 + 2 * kMaxSub) * kTileBytes));
+        configured = true;
+    }
     {
         ProfScope ps(st, PROF_ATTN, 4.0 * B * A * S * S * kHd, 1);
-        attn_fwd_kernel<<<grid, 128, 0, st>>>(p);
+        attn_fwd_kernel<<<grid, 128, smem, st>>>(p, nsub);
     }
     VB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
+
+static int g_bwd_minb = 3;
 
 int attn_bwd(const void* qkv, const float* mask_bias, const void* ctx, const float* lse, const void* dctx,
              void* dqkv, float* drow, int B, int S, int A, int H, float dropout_p, unsigned long long seed,
@@ -542,15 +630,25 @@ int attn_bwd(const void* qkv, const float* mask_bias, const void* ctx, const flo
     if (rc) return rc;
     static bool configured = false;
     if (!configured) {
-        VB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * kTileBytes));
-        VB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * kTileBytes));
+        VB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (3 + 2 * kMaxSub) * kTileBytes));
+        VB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (3 + 2 * kMaxSub) * kTileBytes));
+        VB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 + 2 * kMaxSub) * kTileBytes));
+        VB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 + 2 * kMaxSub) * kTileBytes));
+        const char* e = getenv("VB_ATTN_BWD_MINB");  // tuning knob: resident CTAs per SM the backward kernels are compiled for
+        if (e != nullptr) g_bwd_minb = atoi(e) == 2 ? 2 : 3;
         configured = true;
     }
     dim3 grid((S + kBlk - 1) / kBlk, A, B);
+    const int nsub = static_cast<int>(grid.x) < kMaxSub ? static_cast<int>(grid.x) : kMaxSub;
     {
         ProfScope ps(st, PROF_ATTN, 8.0 * B * A * S * S * kHd, 2);  // algorithmic: 2x forward
-        attn_bwd_dq_kernel<<<grid, 128, 7 * kTileBytes, st>>>(p);
-        attn_bwd_dkv_kernel<<<grid, 128, 6 * kTileBytes, st>>>(p);
+        if (g_bwd_minb == 2) {
+            attn_bwd_dq_kernel<2><<<grid, 128, (3 + 2 * nsub) * kTileBytes, st>>>(p, nsub);
+            attn_bwd_dkv_kernel<2><<<grid, 128, (2 + 2 * nsub) * kTileBytes, st>>>(p, nsub);
+        } else {
+            attn_bwd_dq_kernel<3><<<grid, 128, (3 + 2 * nsub) * kTileBytes, st>>>(p, nsub);
+            attn_bwd_dkv_kernel<3><<<grid, 128, (2 + 2 * nsub) * kTileBytes, st>>>(p, nsub);
+        }
     }
     VB_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -118,38 +118,33 @@ __device__ __forceinline__ float gelu_bwd(float x) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// counter-based dropout RNG (Philox4x32-10): keyed by (seed, stream id) and a 64-bit element
-// counter, so forward and backward regenerate the same keep-mask without storing it.
+// counter-based dropout RNG: a pure function of (seed, stream id, element index), so forward and
+// backward regenerate the same keep-mask without storing it. One 32-bit avalanche hash (lowbias32
+// finaliser, ~8 integer ops) yields two 16-bit uniforms, i.e. 4 ops per element — the epilogues that
+// apply dropout are ALU-bound, a 10-round Philox (13 ops per element) measurably slowed them down.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                               uint32_t k0, uint32_t k1) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    return make_uint4(c0, c1, c2, c3);
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du;
+    x ^= x >> 15; x *= 0x846ca68bu;
+    x ^= x >> 16;
+    return x;
 }
-
+__device__ __forceinline__ uint32_t dropout_key(uint64_t seed, uint32_t stream) {
+    return mix32(static_cast<uint32_t>(seed) ^ mix32(static_cast<uint32_t>(seed >> 32) + 0x9E3779B9u * (stream + 1u)));
+}
 // Keep-mask bits for the 8 consecutive elements starting at flat element index `elem8 * 8`.
 // Each element consumes 16 random bits; kept iff bits >= thresh16 (thresh16 = round(p * 65536)).
 __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint32_t stream, uint64_t elem8,
                                                   uint32_t thresh16) {
-    const uint4 r = philox4x32_10(static_cast<uint32_t>(elem8), static_cast<uint32_t>(elem8 >> 32),
-                                  stream, 0x5eedu, static_cast<uint32_t>(seed),
-                                  static_cast<uint32_t>(seed >> 32));
+    const uint32_t key = dropout_key(seed, stream) ^ (static_cast<uint32_t>(elem8 >> 30) * 0x27d4eb2fu);
+    const uint32_t base = static_cast<uint32_t>(elem8) << 2;
     uint32_t m = 0;
-    m |= ((r.x & 0xffffu) >= thresh16) << 0;
-    m |= ((r.x >> 16) >= thresh16) << 1;
-    m |= ((r.y & 0xffffu) >= thresh16) << 2;
-    m |= ((r.y >> 16) >= thresh16) << 3;
-    m |= ((r.z & 0xffffu) >= thresh16) << 4;
-    m |= ((r.z >> 16) >= thresh16) << 5;
-    m |= ((r.w & 0xffffu) >= thresh16) << 6;
-    m |= ((r.w >> 16) >= thresh16) << 7;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t r = mix32((base + i) ^ key);
+        m |= static_cast<uint32_t>((r & 0xffffu) >= thresh16) << (2 * i);
+        m |= static_cast<uint32_t>((r >> 16) >= thresh16) << (2 * i + 1);
+    }
     return m;
 }
 
@@ -266,6 +261,18 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
           "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr)
         : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");

@@ -6,7 +6,7 @@
 //   warp 1     MMA issuer    (one elected thread issues tcgen05.mma 128xBNx16, accumulators in TMEM,
 //                             two accumulator stages so the epilogue of tile i overlaps tile i+1)
 //   warp 2     TMEM allocator
-//   warps 4-11 epilogue      (tcgen05.ld -> bias / dropout / residual / GELU / GELU' -> 16-byte stores,
+//   warps 4-11 epilogue      (pipelined tcgen05.ld -> bias / dropout / residual / GELU / GELU' -> 32-byte stores,
 //                             or fp32 red.add for split-K weight gradients)
 //
 // Replaces every nn.Linear on the path (reference modeling.py:232-234 Q/K/V, 271 attention output,
@@ -84,7 +84,8 @@ struct Cfg {
     static constexpr int BAR_OFF = kStages * STAGE_BYTES;
     static constexpr int NUM_BARS = 2 * kStages + 4;
     static constexpr int TMEM_PTR_OFF = BAR_OFF + NUM_BARS * 8;
-    static constexpr int SMEM_BYTES = TMEM_PTR_OFF + 16 + 1024;  // +1024: manual 1 KB alignment
+    static constexpr int BIAS_OFF = TMEM_PTR_OFF + 16;           // 2 accumulator stages x BLOCK_N fp32
+    static constexpr int SMEM_BYTES = BIAS_OFF + 2 * BLOCK_N * 4 + 1024;  // +1024: manual 1 KB alignment
     static constexpr int TMEM_COLS = 2 * BLOCK_N;                // power of two: 256 or 512
 };
 
@@ -158,12 +159,13 @@ __device__ __forceinline__ void store16_bf16(bf16* p, const float (&f)[16]) {
     stg_v8(p, r);
 }
 
+// `sbias` points at the 16 staged bias values of these columns in shared memory (or nullptr).
 template <bool OUT_F32>
-__device__ __forceinline__ void epilogue16(const GemmParams& p, int row, int col, float (&x)[16]) {
-    if (p.bias != nullptr) {
+__device__ __forceinline__ void epilogue16(const GemmParams& p, int row, int col, const float* sbias, float (&x)[16]) {
+    if (sbias != nullptr) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4 * i));
+            const float4 b = *reinterpret_cast<const float4*>(sbias + 4 * i);  // warp-uniform address: broadcast
             x[4 * i] += b.x; x[4 * i + 1] += b.y; x[4 * i + 2] += b.z; x[4 * i + 3] += b.w;
         }
     }
@@ -321,36 +323,47 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int ew = warp - 4;
         const int q = warp & 3;   // TMEM lane quarter this warp may access
         const int half = ew >> 2; // which half of the tile's columns
+        const int et = threadIdx.x - 128;  // 0..255 among the epilogue threads
+        float* sbias_all = reinterpret_cast<float*>(smem + C::BIAS_OFF);
+        constexpr int NCH = BLOCK_N / 2 / 16;  // 16-column chunks per warp
         int it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const TileCoord tc = decode_tile(t, n_blocks, p.splits, k_blocks);
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
+            // Stage this tile's bias slice while its MMAs are still running. The barrier is executed on EVERY
+            // tile (uniformly) when a bias exists: passing it proves all epilogue warps finished the previous
+            // tile, so the slab written two tiles later is no longer being read. With split-K the bias
+            // belongs to the whole sum: only split 0 adds it, the other splits stage zeros.
+            const bool has_bias = p.bias != nullptr;
+            float* sb = sbias_all + acc * BLOCK_N;
+            if (has_bias) {
+                const bool mine = p.splits == 1 || (t % p.splits) == 0;
+                for (int i = et; i < BLOCK_N; i += kEpiWarps * 32) {
+                    const int col = tc.n_blk * BLOCK_N + i;
+                    sb[i] = (mine && col < p.N) ? __ldg(p.bias + col) : 0.f;
+                }
+                named_bar_sync(1, kEpiWarps * 32);
+            }
             mbar_wait(tfull_bar(acc), acc_phase);
             tcgen05_fence_after();
             const int row = tc.m_blk * BLOCK_M + q * 32 + lane;
             const int col0 = tc.n_blk * BLOCK_N + half * (BLOCK_N / 2);
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N +
                                     half * (BLOCK_N / 2);
-            // bias belongs to the whole sum: with split-K only split 0 adds it
-            GemmParams pl = p;
-            if (p.splits > 1 && (t % p.splits) != 0) pl.bias = nullptr;
-#pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 2; c += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(taddr0 + c, v);
+            // software pipeline: the TMEM load of chunk k+1 is in flight while chunk k is processed
+            uint32_t v[2][16];
+            tmem_ld_32x32b_x16(taddr0, v[0]);
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
                 tmem_ld_wait();
-                if (row < p.M) {
+                if (k + 1 < NCH) tmem_ld_32x32b_x16(taddr0 + (k + 1) * 16, v[(k + 1) & 1]);
+                const int col = col0 + k * 16;
+                if (row < p.M && col < p.N) {
+                    float x[16];
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const int col = col0 + c + j * 16;
-                        if (col < p.N) {
-                            float x[16];
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[j * 16 + i]);
-                            epilogue16<OUT_F32>(pl, row, col, x);
-                        }
-                    }
+                    for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[k & 1][i]);
+                    epilogue16<OUT_F32>(p, row, col, has_bias ? sb + half * (BLOCK_N / 2) + k * 16 : nullptr, x);
                 }
             }
             tcgen05_fence_before();

@@ -80,63 +80,79 @@ ln_fwd_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict
 // where dx_out = dx (no dropout) or dx * keep / (1-p) (the gradient entering the preceding Linear
 // when its output went through dropout before the residual add; dx itself continues down the
 // residual branch).
+//
+// HBM-bound, so the design goal is bytes in flight: the row is kept as packed bf16 (2 x 16 B per
+// chunk) and unpacked twice instead of living as fp32, gamma and the three column accumulators live
+// in shared memory (one private slab per warp: plain float4 read-modify-write, no atomics, no bank
+// conflicts thanks to the split lo/hi float4 layout), which brings the kernel to ~80 registers and
+// 3 blocks (24 warps, 144 x 512 B loads in flight) per SM.
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 u;
+    u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+    u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+    return u;
+}
+// float4 slot of (array a, chunk ch, half h) inside a slab of `chunks` chunks: lanes -> consecutive 16 B
+__device__ __forceinline__ int slot(int a, int h, int ch, int chunks) { return (a * 2 + h) * chunks + ch; }
+
 template <int NC>
-__global__ void __launch_bounds__(kLnWarps * 32)
+__global__ void __launch_bounds__(kLnWarps * 32, 3)
 ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ gamma, bf16* __restrict__ dx,
               bf16* __restrict__ dx_drop, float* __restrict__ dgamma, float* __restrict__ dbeta,
               float* __restrict__ dbias, int rows, int H, float drop_scale, unsigned drop_thresh16,
               unsigned long long drop_seed, unsigned drop_stream, float in_scale, unsigned in_thresh16,
               unsigned in_stream) {
-    extern __shared__ float red[];  // [3][H]
+    extern __shared__ float4 sm4[];  // [gamma: 2*chunks] [warp][3 arrays][2 halves][chunks]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chunks = H >> 3;
-    for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) red[i] = 0.f;
+    float4* sgam = sm4;
+    float4* acc = sm4 + 2 * chunks + warp * 6 * chunks;
+    for (int i = threadIdx.x; i < 2 * chunks; i += blockDim.x) {
+        const int h = i / chunks, ch = i % chunks;
+        sgam[i] = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8 + h * 4));
+    }
+    for (int i = threadIdx.x; i < kLnWarps * 6 * chunks; i += blockDim.x) sm4[2 * chunks + i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
 
-    float gam[NC][8], ag[NC][8], ab[NC][8], ad[NC][8];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-        const int ch = lane + c * 32;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            gam[c][i] = (ch < chunks) ? __ldg(gamma + ch * 8 + i) : 0.f;
-            ag[c][i] = ab[c][i] = ad[c][i] = 0.f;
-        }
-    }
     const float invH = 1.0f / H;
     for (int row = blockIdx.x * kLnWarps + warp; row < rows; row += gridDim.x * kLnWarps) {
+        uint4 ux[NC], ud[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const int ch = lane + c * 32;
+            if (ch < chunks) {
+                ux[c] = ldg_v4(x + static_cast<long long>(row) * H + ch * 8);
+                ud[c] = ldg_v4(dy + static_cast<long long>(row) * H + ch * 8);
+            }
+        }
         const float mu = mean[row], rs = rstd[row];
-        float xh[NC][8], g[NC][8];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             const int ch = lane + c * 32;
             if (ch < chunks) {
-                const uint4 ux = ldg_v4(x + static_cast<long long>(row) * H + ch * 8);
-                const uint4 ud = ldg_v4(dy + static_cast<long long>(row) * H + ch * 8);
-                const float2 x0 = unpack_bf16x2(ux.x), x1 = unpack_bf16x2(ux.y), x2 = unpack_bf16x2(ux.z), x3 = unpack_bf16x2(ux.w);
-                const float2 d0 = unpack_bf16x2(ud.x), d1 = unpack_bf16x2(ud.y), d2 = unpack_bf16x2(ud.z), d3 = unpack_bf16x2(ud.w);
-                const float xv[8] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y, x3.x, x3.y};
-                float dv[8] = {d0.x, d0.y, d1.x, d1.y, d2.x, d2.y, d3.x, d3.y};
+                float xv[8], dv[8];
+                unpack8(ux[c], xv);
+                unpack8(ud[c], dv);
                 if (in_scale != 0.f) {  // dy is the gradient of dropout(LN(x)): re-apply the keep mask
                     const unsigned long long e8 = (static_cast<unsigned long long>(row) * static_cast<unsigned>(H) + ch * 8) >> 3;
                     const uint32_t keep = dropout_keep8(drop_seed, in_stream, e8, in_thresh16);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) dv[i] = ((keep >> i) & 1u) ? dv[i] * in_scale : 0.f;
                 }
+                const float4 g0 = sgam[ch], g1 = sgam[chunks + ch];
+                const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    xh[c][i] = (xv[i] - mu) * rs;
-                    g[c][i] = dv[i] * gam[c][i];
-                    s1 += g[c][i];
-                    s2 += g[c][i] * xh[c][i];
-                    ag[c][i] += dv[i] * xh[c][i];
-                    ab[c][i] += dv[i];
+                    const float g = dv[i] * gm[i];
+                    s1 += g;
+                    s2 += g * ((xv[i] - mu) * rs);
                 }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { xh[c][i] = 0.f; g[c][i] = 0.f; }
             }
         }
         const float c1 = warp_sum(s1) * invH, c2 = warp_sum(s2) * invH;
@@ -144,45 +160,51 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
         for (int c = 0; c < NC; ++c) {
             const int ch = lane + c * 32;
             if (ch < chunks) {
-                float o[8];
+                float xv[8], dv[8], o[8];
+                unpack8(ux[c], xv);
+                unpack8(ud[c], dv);
+                if (in_scale != 0.f) {
+                    const unsigned long long e8 = (static_cast<unsigned long long>(row) * static_cast<unsigned>(H) + ch * 8) >> 3;
+                    const uint32_t keep = dropout_keep8(drop_seed, in_stream, e8, in_thresh16);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = rs * (g[c][i] - c1 - xh[c][i] * c2);
-                uint4 u;
-                u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
-                u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
-                stg_v4(dx + static_cast<long long>(row) * H + ch * 8, u);
+                    for (int i = 0; i < 8; ++i) dv[i] = ((keep >> i) & 1u) ? dv[i] * in_scale : 0.f;
+                }
+                const float4 g0 = sgam[ch], g1 = sgam[chunks + ch];
+                const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    xv[i] = (xv[i] - mu) * rs;  // xhat
+                    o[i] = rs * (dv[i] * gm[i] - c1 - xv[i] * c2);
+                }
+                stg_v4(dx + static_cast<long long>(row) * H + ch * 8, pack8(o));
                 if (dx_drop != nullptr) {
                     const unsigned long long e8 = (static_cast<unsigned long long>(row) * static_cast<unsigned>(H) + ch * 8) >> 3;
                     const uint32_t keep = dropout_keep8(drop_seed, drop_stream, e8, drop_thresh16);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) o[i] = ((keep >> i) & 1u) ? o[i] * drop_scale : 0.f;
-                    u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
-                    u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
-                    stg_v4(dx_drop + static_cast<long long>(row) * H + ch * 8, u);
+                    stg_v4(dx_drop + static_cast<long long>(row) * H + ch * 8, pack8(o));
                 }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) ad[c][i] += o[i];
-            }
-        }
-    }
-    // block reduction through shared memory, then one global atomic per column
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-        const int ch = lane + c * 32;
-        if (ch < chunks) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                atomicAdd(&red[ch * 8 + i], ag[c][i]);
-                atomicAdd(&red[H + ch * 8 + i], ab[c][i]);
-                atomicAdd(&red[2 * H + ch * 8 + i], ad[c][i]);
+                float4 a;
+                a = acc[slot(0, 0, ch, chunks)]; a.x += dv[0] * xv[0]; a.y += dv[1] * xv[1]; a.z += dv[2] * xv[2]; a.w += dv[3] * xv[3]; acc[slot(0, 0, ch, chunks)] = a;
+                a = acc[slot(0, 1, ch, chunks)]; a.x += dv[4] * xv[4]; a.y += dv[5] * xv[5]; a.z += dv[6] * xv[6]; a.w += dv[7] * xv[7]; acc[slot(0, 1, ch, chunks)] = a;
+                a = acc[slot(1, 0, ch, chunks)]; a.x += dv[0]; a.y += dv[1]; a.z += dv[2]; a.w += dv[3]; acc[slot(1, 0, ch, chunks)] = a;
+                a = acc[slot(1, 1, ch, chunks)]; a.x += dv[4]; a.y += dv[5]; a.z += dv[6]; a.w += dv[7]; acc[slot(1, 1, ch, chunks)] = a;
+                a = acc[slot(2, 0, ch, chunks)]; a.x += o[0]; a.y += o[1]; a.z += o[2]; a.w += o[3]; acc[slot(2, 0, ch, chunks)] = a;
+                a = acc[slot(2, 1, ch, chunks)]; a.x += o[4]; a.y += o[5]; a.z += o[6]; a.w += o[7]; acc[slot(2, 1, ch, chunks)] = a;
             }
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < H; i += blockDim.x) {
-        if (dgamma) atomicAdd(dgamma + i, red[i]);
-        if (dbeta) atomicAdd(dbeta + i, red[H + i]);
-        if (dbias) atomicAdd(dbias + i, red[2 * H + i]);
+    // reduce the 8 warp slabs and flush: one global atomic per column per array per block
+    const float* accf = reinterpret_cast<const float*>(sm4 + 2 * chunks);
+    for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) {
+        const int a = i / H, col = i % H;
+        const int ch = col >> 3, h = (col >> 2) & 1, e = col & 3;
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kLnWarps; ++w) s += accf[(w * 6 * chunks + slot(a, h, ch, chunks)) * 4 + e];
+        float* dst = a == 0 ? dgamma : (a == 1 ? dbeta : dbias);
+        if (dst != nullptr) atomicAdd(dst + col, s);
     }
 }
 
@@ -215,14 +237,22 @@ int ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, 
     VB_REQUIRE(rows > 0, "layernorm backward: no rows");
     VB_REQUIRE((dropout_p > 0.f) == (dx_drop != nullptr), "layernorm backward: dx_drop iff dropout_p > 0");
     const int nc = (H / 8 + 31) / 32;
-    int grid = num_sms() * 4;
+    int grid = num_sms() * 3;
     const int need = (rows + kLnWarps - 1) / kLnWarps;
     if (grid > need) grid = need;
     const float scale = dropout_p > 0.f ? 1.0f / (1.0f - dropout_p) : 0.f;
     const unsigned th = static_cast<unsigned>(dropout_p * 65536.0f + 0.5f);
     const float in_scale = in_dropout_p > 0.f ? 1.0f / (1.0f - in_dropout_p) : 0.f;
     const unsigned in_th = static_cast<unsigned>(in_dropout_p * 65536.0f + 0.5f);
-    const size_t smem = 3 * H * sizeof(float);
+    const size_t smem = static_cast<size_t>(2 * (H / 8) + kLnWarps * 6 * (H / 8)) * sizeof(float4);
+    static bool configured = false;
+    if (!configured) {
+        VB_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        VB_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        VB_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        VB_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        configured = true;
+    }
     ProfScope ps(st, PROF_ROWWISE, (dx_drop ? 8.0 : 6.0) * rows * H, 1);
 #define VB_LN_BWD(NC)                                                                                        \
     ln_bwd_kernel<NC><<<grid, kLnWarps * 32, smem, st>>>(                                                    \
