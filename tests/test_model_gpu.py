@@ -167,3 +167,24 @@ def test_unsupported_modes_raise_explicitly():
     with pytest.raises(NotImplementedError):
         TrainVisualBERTObjective(BertConfig.from_dict(synthetic.bert_config_dict(1, 128, 2, 512, vocab=64)), "nlvr",
                                  visual_embedding_dim=64, bypass_transformer=True)
+
+
+def test_direct_gradient_accumulation_matches_autograd_path():
+    """FlatGradSync pre-sets p.grad to views of one flat buffer; the layer/embedding backward then accumulate in place
+    (autograd receives None). Results must equal the default path (fresh buffers returned to autograd)."""
+    from visualbert_b200.parallel import FlatGradSync
+    model, cfg, sd, batch, c, gold = _build("base3_ragged_pretraining")
+    model(**batch)["loss"].backward()
+    want = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    model.zero_grad(set_to_none=True)
+    sync = FlatGradSync(model)
+    q = model.bert.encoder.layer[0].attention.self
+    assert q.query.weight.grad.data_ptr() + q.query.weight.numel() * 4 == q.key.weight.grad.data_ptr()
+    for _ in range(2):  # second pass also checks zero()
+        sync.zero()
+        model(**batch)["loss"].backward()
+        for k, p in model.named_parameters():
+            if k in want:
+                a, b = p.grad.float(), want[k].float()
+                assert (a - b).norm().item() <= 2e-3 * b.norm().item() + 1e-7, k
+    assert sync.flat.data_ptr() <= model.bert.encoder.layer[1].output.dense.weight.grad.data_ptr()

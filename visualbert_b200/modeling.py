@@ -167,6 +167,10 @@ class BertLayer(nn.Module):
                 a.output.LayerNorm.weight, a.output.LayerNorm.bias, self.intermediate.dense.weight,
                 self.intermediate.dense.bias, o.dense.weight, o.dense.bias, o.LayerNorm.weight, o.LayerNorm.bias)
 
+    def _vb_adjacent_param_groups(self):
+        a = self.attention.self
+        return ((a.query.weight, a.key.weight, a.value.weight), (a.query.bias, a.key.bias, a.value.bias))
+
     def forward(self, hidden_states, attention_mask, seed=0):
         """hidden_states [B, S, H]; attention_mask: the fp32 additive key bias [B, S]
         ((1 - mask) * -10000), or the reference's extended mask [B, 1, 1, S]."""

@@ -78,6 +78,22 @@ def mask_bias(input_mask, image_mask):
     return out
 
 
+def _grad_targets(params, adjacent_groups=()):
+    """Direct-accumulate mode: when every parameter already owns a contiguous fp32 `.grad` (e.g. views of a
+    FlatGradSync buffer) — and the parameters of each adjacent group are laid out back to back — the kernels add
+    their results straight into those buffers (all gradient outputs of the C ABI are `+=`), and autograd gets
+    None. Otherwise returns None and the caller allocates fresh zero buffers for autograd to accumulate."""
+    for p in params:
+        g = p.grad
+        if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.device != p.device or g.shape != p.shape:
+            return None
+    for group in adjacent_groups:
+        for a, b in zip(group[:-1], group[1:]):
+            if a.grad.data_ptr() + a.grad.numel() * 4 != b.grad.data_ptr():
+                return None
+    return [p.grad for p in params]
+
+
 class LayerWeights:
     """bf16 compute copies of one BertLayer's matrices, refreshed when the fp32 masters change."""
 
@@ -142,6 +158,7 @@ class _LayerFn(torch.autograd.Function):
                                            ctypes.byref(a), _stream()), "vb_layer_fwd")
         ctx.meta = meta
         ctx.acts = acts
+        ctx.params = (qw, qb, kw, kb, vw, vb, ow, ob, g1, b1, iw, ib, dw, db, g2, b2)
         ctx.weights = (wqkv, wo, wi, wout, bqkv)
         ctx.weight_key = meta["cache"].key
         ctx.save_for_backward(x, mbias, ob, g1, b1, ib, db, g2, b2)
@@ -159,11 +176,17 @@ class _LayerFn(torch.autograd.Function):
         M, A = B * S, meta["heads"]
         dev = x.device
         dy = dy.to(_BF16).contiguous()
-        sizes = [3 * H * H, 3 * H, H * H, H, H, H, I * H, I, H * I, H, H, H]
-        flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
-        parts = list(torch.split(flat, sizes))
+        qw, qb, kw, kb, vw, vb, ow, ob_, g1_, b1_, iw, ib_, dw, db_, g2_, b2_ = ctx.params
+        direct = _grad_targets(ctx.params, ((qw, kw, vw), (qb, kb, vb)))
         gnames = ("dw_qkv", "db_qkv", "dw_attn_out", "db_attn_out", "dln1_gamma", "dln1_beta",
                   "dw_inter", "db_inter", "dw_out", "db_out", "dln2_gamma", "dln2_beta")
+        if direct is not None:
+            tg = dict(zip(("qw", "qb", "kw", "kb", "vw", "vb", "ow", "ob", "g1", "b1", "iw", "ib", "dw", "db", "g2", "b2"), direct))
+            parts = [tg["qw"], tg["qb"], tg["ow"], tg["ob"], tg["g1"], tg["b1"], tg["iw"], tg["ib"], tg["dw"], tg["db"], tg["g2"], tg["b2"]]
+        else:
+            sizes = [3 * H * H, 3 * H, H * H, H, H, H, I * H, I, H * I, H, H, H]
+            flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
+            parts = list(torch.split(flat, sizes))
         g = _lib.LayerGrads(**{n: t.data_ptr() for n, t in zip(gnames, parts)})
         hd = meta["hidden_dropout"] > 0
         w = _scratch(dev, M, H, I, B, A, S, hd)
@@ -181,6 +204,8 @@ class _LayerFn(torch.autograd.Function):
                                            ctypes.c_void_p(dy.data_ptr()), ctypes.c_void_p(dx.data_ptr()),
                                            ctypes.byref(g), ctypes.byref(sc), _stream()), "vb_layer_bwd")
         ctx.acts = None
+        if direct is not None:
+            return (dx, None, None) + (None,) * 16
         dwqkv, dbqkv, dwo, dbo, dg1, db1, dwi, dbi, dwout, dbout, dg2, db2 = parts
         dwq, dwk, dwv = dwqkv.view(3, H, H).unbind(0)
         dbq, dbk, dbv = dbqkv.view(3, H).unbind(0)
@@ -248,6 +273,7 @@ class _EmbedFn(torch.autograd.Function):
         ctx.feats_need_grad = feats is not None and feats.requires_grad
         ctx.feats_dtype = None if feats is None else feats.dtype
         ctx.feats_shape = None if feats is None else feats.shape
+        ctx.params = (word, pos, typ, typ_vis, pos_vis, pw, pb, gamma, beta)
         ctx.save_for_backward(ids, tt, vt, fb, wp, pb, word, pos, typ, typ_vis, pos_vis, gamma, beta, pre, mean, rstd)
         return y
 
@@ -260,21 +286,25 @@ class _EmbedFn(torch.autograd.Function):
         M = B * (T + V)
         dy = dy.to(_BF16).contiguous()
         f32 = torch.float32
-        dword = torch.zeros_like(word, dtype=f32)
-        dpos = torch.zeros_like(pos, dtype=f32)
-        dtyp = torch.zeros_like(typ, dtype=f32)
-        dtyp_vis = torch.zeros_like(typ_vis, dtype=f32)
-        dpos_vis = torch.zeros_like(pos_vis, dtype=f32)
-        dgamma = torch.zeros_like(gamma, dtype=f32)
-        dbeta = torch.zeros_like(beta, dtype=f32)
+        direct = _grad_targets(ctx.params) if V > 0 else None
+        if direct is not None:
+            dword, dpos, dtyp, dtyp_vis, dpos_vis, dpw, dpb, dgamma, dbeta = direct
+        else:
+            dword = torch.zeros_like(word, dtype=f32)
+            dpos = torch.zeros_like(pos, dtype=f32)
+            dtyp = torch.zeros_like(typ, dtype=f32)
+            dtyp_vis = torch.zeros_like(typ_vis, dtype=f32)
+            dpos_vis = torch.zeros_like(pos_vis, dtype=f32)
+            dgamma = torch.zeros_like(gamma, dtype=f32)
+            dbeta = torch.zeros_like(beta, dtype=f32)
+            dpw = torch.zeros(H, Dv, device=dev, dtype=f32) if V > 0 else None
+            dpb = torch.zeros(H, device=dev, dtype=f32) if V > 0 else None
         d_pre = torch.empty(M, H, device=dev, dtype=_BF16)
         if V > 0:
-            dpw = torch.zeros(H, Dv, device=dev, dtype=f32)
-            dpb = torch.zeros(H, device=dev, dtype=f32)
             d_vis = torch.empty(B * V, H, device=dev, dtype=_BF16)
             d_feats = torch.empty(B * V, Dv, device=dev, dtype=_BF16) if ctx.feats_need_grad else None
         else:
-            dpw = dpb = d_vis = d_feats = None
+            d_vis = d_feats = None
         d = _lib.EmbedDesc(
             batch=B, text_len=T, num_regions=V, hidden=H, visual_dim=Dv, vocab=word.shape[0], max_pos=pos.shape[0],
             n_types=typ.shape[0], eps=1e-12, dropout=meta["dropout"], seed=meta["seed"],
@@ -291,6 +321,8 @@ class _EmbedFn(torch.autograd.Function):
         dfe = None
         if d_feats is not None:
             dfe = d_feats.view(ctx.feats_shape).to(ctx.feats_dtype)
+        if direct is not None:
+            return (None, None, None, None, dfe) + (None,) * 9
         return (None, None, None, None, dfe, dword, dpos, dtyp, dtyp_vis, dpos_vis, dpw, dpb, dgamma, dbeta)
 
 

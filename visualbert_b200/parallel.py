@@ -14,10 +14,20 @@ import torch.distributed as dist
 class FlatGradSync:
     def __init__(self, module, process_group=None):
         seen, self.params = set(), []
-        for p in module.parameters():
+
+        def add(p):
             if p.requires_grad and id(p) not in seen:  # tied weights appear once
                 seen.add(id(p))
                 self.params.append(p)
+
+        # modules may ask for groups of parameters to be adjacent (BertLayer: query|key|value weights, then
+        # their biases, so the fused [3H, H] weight-gradient GEMM writes straight into this buffer)
+        for m in module.modules():
+            for group in getattr(m, "_vb_adjacent_param_groups", lambda: ())():
+                for p in group:
+                    add(p)
+        for p in module.parameters():
+            add(p)
         if not self.params:
             raise ValueError("FlatGradSync: module has no trainable parameters")
         dev = self.params[0].device
