@@ -38,7 +38,7 @@ struct AttnParams {
     int B, S, A, H;
     float scale;       // 1/sqrt(head_dim)
     float drop_scale;  // 1/(1-p) or 0
-    unsigned drop_thresh16;
+    unsigned drop_thresh16;  // attention: 8-bit threshold, round(p * 256)
     unsigned drop_seed;
 };
 
@@ -98,11 +98,12 @@ __device__ __forceinline__ void load_afrag(uint32_t (&a)[4][4], uint32_t tile, i
 // rows of T (n index) carry data — whole 16-wide n pairs beyond it are skipped (warp-uniform).
 __device__ __forceinline__ void gemm_nt(float (&acc)[8][4], const uint32_t (&a)[4][4], uint32_t tile, int lane,
                                         int nvalid = 64) {
+    // k-step outermost: consecutive MMAs hit different accumulators (no back-to-back dependent HMMA)
 #pragma unroll
-    for (int np = 0; np < 4; ++np) {
-        if (np * 16 < nvalid) {
+    for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
+        for (int np = 0; np < 4; ++np) {
+            if (np * 16 < nvalid) {
                 const int row = np * 16 + (lane & 7) + (lane >> 4) * 8;
                 const int chunk = ks * 2 + ((lane >> 3) & 1);
                 uint32_t b0, b1, b2, b3;
@@ -136,11 +137,11 @@ __device__ __forceinline__ void gemm_nn(float (&acc)[8][4], const uint32_t (&a)[
 __device__ __forceinline__ void gemm_nt_half(float (&acc)[4][4], const uint32_t (&a)[4][4], uint32_t tile, int lane,
                                              int half, int nvalid) {
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const int np = half * 2 + q;
-        if (np * 16 < nvalid) {
+    for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
+        for (int q = 0; q < 2; ++q) {
+            const int np = half * 2 + q;
+            if (np * 16 < nvalid) {
                 const int row = np * 16 + (lane & 7) + (lane >> 4) * 8;
                 const int chunk = ks * 2 + ((lane >> 3) & 1);
                 uint32_t b0, b1, b2, b3;
@@ -175,13 +176,20 @@ __device__ __forceinline__ void zero_acc(float (&c)[8][4]) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
 }
-// keep decision for attention-probability dropout, a pure function of (head-row index, key)
-__device__ __forceinline__ bool attn_keep(unsigned seed, unsigned bh, int q, int key, int S, unsigned thresh16) {
-    unsigned x = (bh * static_cast<unsigned>(S) + static_cast<unsigned>(q)) * static_cast<unsigned>(S) +
-                 static_cast<unsigned>(key);
-    x ^= seed;
-    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
-    return (x >> 16) >= thresh16;
+// Attention-probability dropout (reference modeling.py:251): keep decisions are a pure function of
+// (batch*head, query, key). One 32-bit hash covers a 2x2 block of (query, key) pairs with 8 random bits each,
+// so every thread — whichever way its fragment is oriented (queries x keys in forward / dQ, keys x queries
+// in dK/dV) — spends one hash per two elements. The drop probability is therefore quantised to
+// round(p * 256) / 256 (0.1 -> 26/256 = 0.1016) and the survivors are scaled by 256 / (256 - that), which
+// keeps E[dropout(P)] = P exactly.
+__device__ __forceinline__ uint32_t attn_hash(unsigned seed, unsigned bh, int q, int key, int S) {
+    const unsigned sh = static_cast<unsigned>(S + 1) >> 1;
+    const unsigned x = (bh * sh + (static_cast<unsigned>(q) >> 1)) * sh + (static_cast<unsigned>(key) >> 1);
+    return mix32(x ^ seed);
+}
+// keep bit of element (q, key) out of the block hash h
+__device__ __forceinline__ bool attn_keep_from(uint32_t h, int q, int key, unsigned thresh8) {
+    return ((h >> ((((q & 1) << 1) | (key & 1)) * 8)) & 0xffu) >= thresh8;
 }
 // store a 16 x 64 accumulator tile as bf16 rows of a [*, ld] matrix (rows >= nrows skipped)
 __device__ __forceinline__ void store_acc(bf16* base, long long ld, int row0, int nrows, const float (&c)[8][4],
@@ -296,12 +304,13 @@ attn_fwd_kernel(const AttnParams p, const int nsub) {
             if (p.drop_scale != 0.f) {
 #pragma unroll
                 for (int nt = 0; nt < 8; ++nt) {
-                    const int key = kb * kBlk + nt * 8 + 2 * t;
+                    const int key = kb * kBlk + nt * 8 + 2 * t;  // even: (key, key+1) share a hash block
                     const int qa = qrow0 + g, qc = qrow0 + g + 8;
-                    s[nt][0] = attn_keep(p.drop_seed, bh, qa, key, S, p.drop_thresh16) ? s[nt][0] * p.drop_scale : 0.f;
-                    s[nt][1] = attn_keep(p.drop_seed, bh, qa, key + 1, S, p.drop_thresh16) ? s[nt][1] * p.drop_scale : 0.f;
-                    s[nt][2] = attn_keep(p.drop_seed, bh, qc, key, S, p.drop_thresh16) ? s[nt][2] * p.drop_scale : 0.f;
-                    s[nt][3] = attn_keep(p.drop_seed, bh, qc, key + 1, S, p.drop_thresh16) ? s[nt][3] * p.drop_scale : 0.f;
+                    const uint32_t ha = attn_hash(p.drop_seed, bh, qa, key, S), hc = attn_hash(p.drop_seed, bh, qc, key, S);
+                    s[nt][0] = attn_keep_from(ha, qa, key, p.drop_thresh16) ? s[nt][0] * p.drop_scale : 0.f;
+                    s[nt][1] = attn_keep_from(ha, qa, key + 1, p.drop_thresh16) ? s[nt][1] * p.drop_scale : 0.f;
+                    s[nt][2] = attn_keep_from(hc, qc, key, p.drop_thresh16) ? s[nt][2] * p.drop_scale : 0.f;
+                    s[nt][3] = attn_keep_from(hc, qc, key + 1, p.drop_thresh16) ? s[nt][3] * p.drop_scale : 0.f;
                 }
             }
             uint32_t pf[4][4];
@@ -426,10 +435,11 @@ attn_bwd_dq_kernel(const AttnParams p, const int nsub) {
                     if (p.drop_scale != 0.f) {
                         const int key = kb * kBlk + nt * 8 + 2 * t;
                         const int qa = qrow0 + g, qc = qrow0 + g + 8;
-                        e0 = attn_keep(p.drop_seed, bh, qa, key, S, p.drop_thresh16) ? e0 * p.drop_scale : 0.f;
-                        e1 = attn_keep(p.drop_seed, bh, qa, key + 1, S, p.drop_thresh16) ? e1 * p.drop_scale : 0.f;
-                        e2 = attn_keep(p.drop_seed, bh, qc, key, S, p.drop_thresh16) ? e2 * p.drop_scale : 0.f;
-                        e3 = attn_keep(p.drop_seed, bh, qc, key + 1, S, p.drop_thresh16) ? e3 * p.drop_scale : 0.f;
+                        const uint32_t ha = attn_hash(p.drop_seed, bh, qa, key, S), hc = attn_hash(p.drop_seed, bh, qc, key, S);
+                        e0 = attn_keep_from(ha, qa, key, p.drop_thresh16) ? e0 * p.drop_scale : 0.f;
+                        e1 = attn_keep_from(ha, qa, key + 1, p.drop_thresh16) ? e1 * p.drop_scale : 0.f;
+                        e2 = attn_keep_from(hc, qc, key, p.drop_thresh16) ? e2 * p.drop_scale : 0.f;
+                        e3 = attn_keep_from(hc, qc, key + 1, p.drop_thresh16) ? e3 * p.drop_scale : 0.f;
                     }
                     s[nt][0] = p0 * (e0 - d0); s[nt][1] = p1 * (e1 - d0);
                     s[nt][2] = p2 * (e2 - d1); s[nt][3] = p3 * (e3 - d1);
@@ -520,11 +530,12 @@ attn_bwd_dkv_kernel(const AttnParams p, const int nsub) {
                 keepbits = 0;
 #pragma unroll
                 for (int nt = 0; nt < 8; ++nt) {
-                    const int q = qb * kBlk + nt * 8 + 2 * t;
-                    keepbits |= static_cast<unsigned>(attn_keep(p.drop_seed, bh, q, ka, S, p.drop_thresh16)) << (nt * 4);
-                    keepbits |= static_cast<unsigned>(attn_keep(p.drop_seed, bh, q + 1, ka, S, p.drop_thresh16)) << (nt * 4 + 1);
-                    keepbits |= static_cast<unsigned>(attn_keep(p.drop_seed, bh, q, kc, S, p.drop_thresh16)) << (nt * 4 + 2);
-                    keepbits |= static_cast<unsigned>(attn_keep(p.drop_seed, bh, q + 1, kc, S, p.drop_thresh16)) << (nt * 4 + 3);
+                    const int q = qb * kBlk + nt * 8 + 2 * t;  // even: (q, q+1) share a hash block
+                    const uint32_t ha = attn_hash(p.drop_seed, bh, q, ka, S), hc = attn_hash(p.drop_seed, bh, q, kc, S);
+                    keepbits |= static_cast<unsigned>(attn_keep_from(ha, q, ka, p.drop_thresh16)) << (nt * 4);
+                    keepbits |= static_cast<unsigned>(attn_keep_from(ha, q + 1, ka, p.drop_thresh16)) << (nt * 4 + 1);
+                    keepbits |= static_cast<unsigned>(attn_keep_from(hc, q, kc, p.drop_thresh16)) << (nt * 4 + 2);
+                    keepbits |= static_cast<unsigned>(attn_keep_from(hc, q + 1, kc, p.drop_thresh16)) << (nt * 4 + 3);
                 }
             }
             const float ds = p.drop_scale != 0.f ? p.drop_scale : 1.f;
@@ -588,8 +599,10 @@ static int fill_params(AttnParams& p, const void* qkv, const float* mask_bias, v
     p.drow = drow;
     p.B = B; p.S = S; p.A = A; p.H = H;
     p.scale = 0.125f;
-    p.drop_scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 0.f;
-    p.drop_thresh16 = static_cast<unsigned>(dropout_p * 65536.f + 0.5f);
+    // 8-bit quantised keep threshold (see attn_hash); the scale uses the quantised probability
+    const unsigned th8 = static_cast<unsigned>(dropout_p * 256.f + 0.5f);
+    p.drop_thresh16 = th8;
+    p.drop_scale = dropout_p > 0.f ? 256.f / (256.f - static_cast<float>(th8 > 255 ? 255 : th8)) : 0.f;
     // fold the per-layer stream id into the 32-bit seed of the element hash
     unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (stream_id + 1ull);
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
