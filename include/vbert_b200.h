@@ -83,14 +83,17 @@ int vb_layernorm_bwd(const void* dy, const void* x, const float* mean, const flo
 
 /* ---- BertSelfAttention core (M.py:241-256) ----------------------------------------------- */
 /* qkv bf16 [batch*seq, 3*hidden] (Q | K | V), mask_bias fp32 [batch, seq] additive key bias,
- * ctx bf16 [batch*seq, hidden], lse fp32 [batch, heads, seq]. head_dim must be 64. */
-int vb_attention_fwd(const void* qkv, const float* mask_bias, void* ctx, float* lse, int32_t batch, int32_t seq,
-                     int32_t heads, int32_t hidden, float dropout_p, uint64_t dropout_seed, uint32_t dropout_stream,
-                     void* stream);
+ * ctx bf16 [batch*seq, hidden], lse fp32 [batch, heads, seq]. head_dim must be 64.
+ * keep_mask: vb_attention_keep_bytes(batch, seq, heads) bytes, written by forward and read by backward when
+ * dropout_p > 0 (packed keep bits of the attention-probability dropout, M.py:251); may be NULL otherwise. */
+int64_t vb_attention_keep_bytes(int32_t batch, int32_t seq, int32_t heads);
+int vb_attention_fwd(const void* qkv, const float* mask_bias, void* ctx, float* lse, void* keep_mask, int32_t batch,
+                     int32_t seq, int32_t heads, int32_t hidden, float dropout_p, uint64_t dropout_seed,
+                     uint32_t dropout_stream, void* stream);
 /* dqkv bf16 [batch*seq, 3*hidden] out; drow fp32 [batch, heads, seq] scratch. */
-int vb_attention_bwd(const void* qkv, const float* mask_bias, const void* ctx, const float* lse, const void* dctx,
-                     void* dqkv, float* drow, int32_t batch, int32_t seq, int32_t heads, int32_t hidden,
-                     float dropout_p, uint64_t dropout_seed, uint32_t dropout_stream, void* stream);
+int vb_attention_bwd(const void* qkv, const float* mask_bias, const void* ctx, const float* lse, const void* keep_mask,
+                     const void* dctx, void* dqkv, float* drow, int32_t batch, int32_t seq, int32_t heads,
+                     int32_t hidden, float dropout_p, uint64_t dropout_seed, uint32_t dropout_stream, void* stream);
 
 /* ---- helpers ----------------------------------------------------------------------------- */
 /* (1 - cat(input_mask, image_mask)) * -10000 -> fp32 [batch, text+regions]  (M.py:1417, 1286-1294);
@@ -132,6 +135,7 @@ typedef struct {
     void* g;     /* [M, I]  gelu(u) */
     void* pre2;  /* [M, H]  output.dense(g) (+dropout) + x1                      (M.py:316-318 before LN) */
     float* mean2; float* rstd2;
+    void* keep_mask; /* vb_attention_keep_bytes(batch, seq, heads) bytes; only touched when attn_dropout > 0 */
 } vb_layer_acts;
 
 /* fp32 parameter-gradient accumulators (+=), nn.Linear layout */

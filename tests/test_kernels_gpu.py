@@ -149,7 +149,7 @@ def test_attention_fwd_bwd(B, S, A):
     bias = ((1 - mask) * -10000.0).contiguous()
     ctx = torch.empty(B * S, H, device=dev, dtype=torch.bfloat16); lse = torch.empty(B, A, S, device=dev)
     P = lambda t: ctypes.c_void_p(t.data_ptr())
-    _lib.check(L.vb_attention_fwd(P(qkv), P(bias), P(ctx), P(lse), B, S, A, H, ctypes.c_float(0.0), ctypes.c_uint64(0), 0, st), "attn_fwd")
+    _lib.check(L.vb_attention_fwd(P(qkv), P(bias), P(ctx), P(lse), None, B, S, A, H, ctypes.c_float(0.0), ctypes.c_uint64(0), 0, st), "attn_fwd")
     qr = qkv.float().requires_grad_(True)
     ref, lse_ref = _attn_ref(qr, bias, B, S, A, H)
     torch.cuda.synchronize()
@@ -158,7 +158,7 @@ def test_attention_fwd_bwd(B, S, A):
     dctx = torch.randn(B * S, H, device=dev).bfloat16()
     ref.backward(dctx.float())
     dqkv = torch.empty_like(qkv); drow = torch.empty(B, A, S, device=dev)
-    _lib.check(L.vb_attention_bwd(P(qkv), P(bias), P(ctx), P(lse), P(dctx), P(dqkv), P(drow), B, S, A, H,
+    _lib.check(L.vb_attention_bwd(P(qkv), P(bias), P(ctx), P(lse), None, P(dctx), P(dqkv), P(drow), B, S, A, H,
                                   ctypes.c_float(0.0), ctypes.c_uint64(0), 0, st), "attn_bwd")
     torch.cuda.synchronize()
     g = qr.grad
@@ -177,7 +177,7 @@ def test_attention_fully_masked_example_stays_finite():
     bias = torch.zeros(B, S, device=dev); bias[1] = -10000.0
     ctx = torch.empty(B * S, H, device=dev, dtype=torch.bfloat16); lse = torch.empty(B, A, S, device=dev)
     P = lambda t: ctypes.c_void_p(t.data_ptr())
-    _lib.check(L.vb_attention_fwd(P(qkv), P(bias), P(ctx), P(lse), B, S, A, H, ctypes.c_float(0.0), ctypes.c_uint64(0), 0, st), "attn_fwd")
+    _lib.check(L.vb_attention_fwd(P(qkv), P(bias), P(ctx), P(lse), None, B, S, A, H, ctypes.c_float(0.0), ctypes.c_uint64(0), 0, st), "attn_fwd")
     ref, _ = _attn_ref(qkv, bias, B, S, A, H)
     torch.cuda.synchronize()
     assert _rel(ctx, ref) < BF16_TOL
@@ -194,15 +194,23 @@ def test_attention_dropout_consistent_between_fwd_and_bwd():
     P = lambda t: ctypes.c_void_p(t.data_ptr())
     ctx = torch.empty(B * S, H, device=dev, dtype=torch.bfloat16); lse = torch.empty(B, A, S, device=dev)
     args = (ctypes.c_float(0.2), ctypes.c_uint64(99), 5, st)
-    _lib.check(L.vb_attention_fwd(P(qkv), P(bias), P(ctx), P(lse), B, S, A, H, *args), "attn_fwd")
+    L.vb_attention_keep_bytes.restype = ctypes.c_int64
+    keep = torch.zeros(int(L.vb_attention_keep_bytes(B, S, A)), device=dev, dtype=torch.uint8)
+    keep2 = torch.zeros_like(keep)
+    _lib.check(L.vb_attention_fwd(P(qkv), P(bias), P(ctx), P(lse), P(keep), B, S, A, H, *args), "attn_fwd")
     ctx2 = torch.empty_like(ctx)
-    _lib.check(L.vb_attention_fwd(P(qkv), P(bias), P(ctx2), P(lse), B, S, A, H, *args), "attn_fwd")
+    _lib.check(L.vb_attention_fwd(P(qkv), P(bias), P(ctx2), P(lse), P(keep2), B, S, A, H, *args), "attn_fwd")
     ref, _ = _attn_ref(qkv, bias, B, S, A, H)
     dctx = torch.randn(B * S, H, device=dev).bfloat16()
     dqkv = torch.empty_like(qkv); drow = torch.empty(B, A, S, device=dev)
-    _lib.check(L.vb_attention_bwd(P(qkv), P(bias), P(ctx), P(lse), P(dctx), P(dqkv), P(drow), B, S, A, H, *args), "attn_bwd")
+    _lib.check(L.vb_attention_bwd(P(qkv), P(bias), P(ctx), P(lse), P(keep), P(dctx), P(dqkv), P(drow), B, S, A, H, *args), "attn_bwd")
     torch.cuda.synchronize()
-    assert torch.equal(ctx, ctx2)
+    assert torch.equal(ctx, ctx2) and torch.equal(keep, keep2)
+    # stored keep-mask: valid (query < S, key < S) bits are ~80 % ones for p = 0.2 (quantised to 51/256)
+    nkb = (S + 63) // 64
+    words = keep.view(torch.int64).view(B * A, nkb * 64, nkb)[:, :S, :]
+    bits = ((words.unsqueeze(-1) >> torch.arange(64, device=dev)) & 1).reshape(B * A, S, nkb * 64)[:, :, :S]
+    assert abs(bits.float().mean().item() - (1 - 51 / 256)) < 5e-3
     assert _rel(ctx, ref) > 0.05  # dropout really changed the output
     # O is linear in V: sum(dO * O) == sum(dV * V)
     lhs = (dctx.float() * ctx.float()).sum().item()

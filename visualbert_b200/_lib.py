@@ -43,7 +43,7 @@ LayerDesc = _struct("LayerDesc", [
     ("b_qkv", _P), ("b_attn_out", _P), ("ln1_gamma", _P), ("ln1_beta", _P),
     ("b_inter", _P), ("b_out", _P), ("ln2_gamma", _P), ("ln2_beta", _P), ("mask_bias", _P)])
 LayerActs = _struct("LayerActs", [(n, _P) for n in (
-    "qkv", "ctx", "lse", "pre1", "mean1", "rstd1", "x1", "u", "g", "pre2", "mean2", "rstd2")])
+    "qkv", "ctx", "lse", "pre1", "mean1", "rstd1", "x1", "u", "g", "pre2", "mean2", "rstd2", "keep_mask")])
 LayerGrads = _struct("LayerGrads", [(n, _P) for n in (
     "dw_qkv", "db_qkv", "dw_attn_out", "db_attn_out", "dln1_gamma", "dln1_beta",
     "dw_inter", "db_inter", "dw_out", "db_out", "dln2_gamma", "dln2_beta")])
@@ -63,7 +63,7 @@ EmbedGrads = _struct("EmbedGrads", [(n, _P) for n in (
 # every symbol include/vbert_b200.h declares (checked by tests/test_abi.py without a GPU)
 EXPORTS = [
     "vb_abi_version", "vb_last_error", "vb_launch_count", "vb_profile_enable", "vb_profile_read", "vb_gemm", "vb_layernorm_fwd", "vb_layernorm_bwd",
-    "vb_attention_fwd", "vb_attention_bwd", "vb_mask_bias", "vb_cast_f32_to_bf16", "vb_cast_bf16_to_f32",
+    "vb_attention_keep_bytes", "vb_attention_fwd", "vb_attention_bwd", "vb_mask_bias", "vb_cast_f32_to_bf16", "vb_cast_bf16_to_f32",
     "vb_colsum_bf16", "vb_layer_fwd", "vb_layer_bwd", "vb_embed_fwd", "vb_embed_bwd",
 ]
 
@@ -87,6 +87,7 @@ def lib():
         h.vb_last_error.restype = ctypes.c_char_p
         h.vb_launch_count.restype = ctypes.c_int64
         h.vb_abi_version.restype = ctypes.c_int
+        h.vb_attention_keep_bytes.restype = ctypes.c_int64
         _lib = h
     return _lib
 

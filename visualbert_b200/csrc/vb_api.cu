@@ -69,7 +69,7 @@ int layer_fwd(const vb_layer_desc* d, const void* x_in, void* x_out, const vb_la
     vb_gemm_args a = fwd_args(x_in, d->w_qkv, s->qkv, M, 3 * H, H);
     a.bias = d->b_qkv;
     VB_TRY(gemm(a, st));
-    VB_TRY(attn_fwd(s->qkv, d->mask_bias, s->ctx, s->lse, d->batch, d->seq, d->heads, H, d->attn_dropout, d->seed,
+    VB_TRY(attn_fwd(s->qkv, d->mask_bias, s->ctx, s->lse, s->keep_mask, d->batch, d->seq, d->heads, H, d->attn_dropout, d->seed,
                     drop_stream(d->layer_index, kSiteAttnProbs), st));
     a = fwd_args(s->ctx, d->w_attn_out, s->pre1, M, H, H);
     a.bias = d->b_attn_out; a.addend = x_in; a.ld_add = H;
@@ -117,7 +117,7 @@ int layer_bwd(const vb_layer_desc* d, const void* x_in, const vb_layer_acts* s, 
     VB_TRY(gemm(wgrad_args(dpm, s->ctx, g->dw_attn_out, M, H, H), st));
     VB_TRY(gemm(dgrad_args(dpm, d->w_attn_out, w->d_ctx, M, H, H), st));
     // ---- BertSelfAttention ----
-    VB_TRY(attn_bwd(s->qkv, d->mask_bias, s->ctx, s->lse, w->d_ctx, w->d_big, w->drow, d->batch, d->seq, d->heads, H,
+    VB_TRY(attn_bwd(s->qkv, d->mask_bias, s->ctx, s->lse, s->keep_mask, w->d_ctx, w->d_big, w->drow, d->batch, d->seq, d->heads, H,
                     d->attn_dropout, d->seed, drop_stream(d->layer_index, kSiteAttnProbs), st));
     VB_TRY(colsum(w->d_big, 3 * H, g->db_qkv, M, 3 * H, st));
     VB_TRY(gemm(wgrad_args(w->d_big, x_in, g->dw_qkv, M, 3 * H, H), st));

@@ -35,6 +35,7 @@ struct AttnParams {
     const bf16* dctx;  // [B*S, H]        (bwd)
     bf16* dqkv;        // [B*S, 3H]       (bwd out)
     float* drow;       // [B, A, S]       (bwd scratch: rowsum(dO * O))
+    unsigned long long* keep;  // [B*A, nkb*64 rows, nkb] 64-bit keep-masks (bit = key within the 64-key block); dropout only
     int B, S, A, H;
     float scale;       // 1/sqrt(head_dim)
     float drop_scale;  // 1/(1-p) or 0
@@ -176,20 +177,35 @@ __device__ __forceinline__ void zero_acc(float (&c)[8][4]) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
 }
-// Attention-probability dropout (reference modeling.py:251): keep decisions are a pure function of
-// (batch*head, query, key). One 32-bit hash covers a 2x2 block of (query, key) pairs with 8 random bits each,
-// so every thread — whichever way its fragment is oriented (queries x keys in forward / dQ, keys x queries
-// in dK/dV) — spends one hash per two elements. The drop probability is therefore quantised to
-// round(p * 256) / 256 (0.1 -> 26/256 = 0.1016) and the survivors are scaled by 256 / (256 - that), which
-// keeps E[dropout(P)] = P exactly.
-__device__ __forceinline__ uint32_t attn_hash(unsigned seed, unsigned bh, int q, int key, int S) {
-    const unsigned sh = static_cast<unsigned>(S + 1) >> 1;
-    const unsigned x = (bh * sh + (static_cast<unsigned>(q) >> 1)) * sh + (static_cast<unsigned>(key) >> 1);
-    return mix32(x ^ seed);
+// Attention-probability dropout (reference modeling.py:251). The keep decisions are drawn ONCE, in the forward
+// kernel (counter hash of (batch*head, query row, key block, lane quad) -> 4 x 8 random bits per hash), applied
+// there, and written out as a packed bit-mask: one 64-bit word per (query row, 64-key block). Both backward
+// kernels read the bits back instead of re-hashing — the kernels are instruction-issue bound and the per-element
+// hashing was ~45 % of their instruction count. The drop probability is quantised to round(p*256)/256
+// (0.1 -> 26/256) and survivors are scaled by 256/(256 - that), so E[dropout(P)] = P exactly.
+// keep8x2: for one query row, the 16 elements a thread owns in a 64-key block (keys nt*8 + 2t + {0,1}).
+__device__ __forceinline__ uint32_t attn_keep16(unsigned seed, unsigned bh, int q, int kb, int t, int S, unsigned thresh8) {
+    const unsigned base = (((bh * static_cast<unsigned>(S) + static_cast<unsigned>(q)) << 6) + (static_cast<unsigned>(kb) << 4) +
+                           (static_cast<unsigned>(t) << 2));
+    uint32_t bits = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // hash j covers n-tiles 2j and 2j+1
+        const uint32_t h = mix32((base + j) ^ seed);
+        bits |= static_cast<uint32_t>((h & 0xffu) >= thresh8) << (4 * j);
+        bits |= static_cast<uint32_t>(((h >> 8) & 0xffu) >= thresh8) << (4 * j + 1);
+        bits |= static_cast<uint32_t>(((h >> 16) & 0xffu) >= thresh8) << (4 * j + 2);
+        bits |= static_cast<uint32_t>((h >> 24) >= thresh8) << (4 * j + 3);
+    }
+    return bits;  // bit (2*nt + c) = keep of key nt*8 + 2t + c
 }
-// keep bit of element (q, key) out of the block hash h
-__device__ __forceinline__ bool attn_keep_from(uint32_t h, int q, int key, unsigned thresh8) {
-    return ((h >> ((((q & 1) << 1) | (key & 1)) * 8)) & 0xffu) >= thresh8;
+// spread a thread's 16 keep bits to their key positions inside the 64-bit block mask and OR over the quad
+__device__ __forceinline__ unsigned long long quad_mask64(uint32_t bits16, int t) {
+    unsigned long long m = 0;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) m |= static_cast<unsigned long long>((bits16 >> (2 * nt)) & 3u) << (nt * 8 + 2 * t);
+    m |= __shfl_xor_sync(0xffffffffu, m, 1);
+    m |= __shfl_xor_sync(0xffffffffu, m, 2);
+    return m;
 }
 // store a 16 x 64 accumulator tile as bf16 rows of a [*, ld] matrix (rows >= nrows skipped)
 __device__ __forceinline__ void store_acc(bf16* base, long long ld, int row0, int nrows, const float (&c)[8][4],
@@ -302,15 +318,21 @@ attn_fwd_kernel(const AttnParams p, const int nsub) {
                 o[nt][2] *= alpha[1]; o[nt][3] *= alpha[1];
             }
             if (p.drop_scale != 0.f) {
+                const int qa = qrow0 + g, qc = qrow0 + g + 8;
+                const uint32_t ka_bits = attn_keep16(p.drop_seed, bh, qa, kb, t, S, p.drop_thresh16);
+                const uint32_t kc_bits = attn_keep16(p.drop_seed, bh, qc, kb, t, S, p.drop_thresh16);
 #pragma unroll
                 for (int nt = 0; nt < 8; ++nt) {
-                    const int key = kb * kBlk + nt * 8 + 2 * t;  // even: (key, key+1) share a hash block
-                    const int qa = qrow0 + g, qc = qrow0 + g + 8;
-                    const uint32_t ha = attn_hash(p.drop_seed, bh, qa, key, S), hc = attn_hash(p.drop_seed, bh, qc, key, S);
-                    s[nt][0] = attn_keep_from(ha, qa, key, p.drop_thresh16) ? s[nt][0] * p.drop_scale : 0.f;
-                    s[nt][1] = attn_keep_from(ha, qa, key + 1, p.drop_thresh16) ? s[nt][1] * p.drop_scale : 0.f;
-                    s[nt][2] = attn_keep_from(hc, qc, key, p.drop_thresh16) ? s[nt][2] * p.drop_scale : 0.f;
-                    s[nt][3] = attn_keep_from(hc, qc, key + 1, p.drop_thresh16) ? s[nt][3] * p.drop_scale : 0.f;
+                    s[nt][0] = ((ka_bits >> (2 * nt)) & 1u) ? s[nt][0] * p.drop_scale : 0.f;
+                    s[nt][1] = ((ka_bits >> (2 * nt + 1)) & 1u) ? s[nt][1] * p.drop_scale : 0.f;
+                    s[nt][2] = ((kc_bits >> (2 * nt)) & 1u) ? s[nt][2] * p.drop_scale : 0.f;
+                    s[nt][3] = ((kc_bits >> (2 * nt + 1)) & 1u) ? s[nt][3] * p.drop_scale : 0.f;
+                }
+                const unsigned long long ma = quad_mask64(ka_bits, t), mc = quad_mask64(kc_bits, t);
+                if (t == 0) {  // rows are padded to nkb*64 in the mask buffer: no bounds check needed
+                    unsigned long long* kp = p.keep + (static_cast<unsigned long long>(bh) * (nkb * kBlk)) * nkb;
+                    kp[static_cast<long long>(qa) * nkb + kb] = ma;
+                    kp[static_cast<long long>(qc) * nkb + kb] = mc;
                 }
             }
             uint32_t pf[4][4];
@@ -418,6 +440,12 @@ attn_bwd_dq_kernel(const AttnParams p, const int nsub) {
             const int kvalid = min(kBlk, S - kb * kBlk);
             float s[8][4];
             zero_acc(s);
+            unsigned long long keep_a = 0, keep_c = 0;
+            if (p.drop_scale != 0.f) {
+                const unsigned long long* kp = p.keep + (static_cast<unsigned long long>(bh) * (nkb * kBlk)) * nkb;
+                keep_a = kp[static_cast<long long>(qrow0 + g) * nkb + kb];
+                keep_c = kp[static_cast<long long>(qrow0 + g + 8) * nkb + kb];
+            }
             gemm_nt(s, qf, sK0 + j * kTileBytes, lane, kvalid);
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {  // dP = dO V^T in two 32-key halves (register pressure)
@@ -433,13 +461,11 @@ attn_bwd_dq_kernel(const AttnParams p, const int nsub) {
                     const float p2 = fast_ex2(fmaf(s[nt][2], sc2, b0) - lse1), p3 = fast_ex2(fmaf(s[nt][3], sc2, b1) - lse1);
                     float e0 = dp[n4][0], e1 = dp[n4][1], e2 = dp[n4][2], e3 = dp[n4][3];
                     if (p.drop_scale != 0.f) {
-                        const int key = kb * kBlk + nt * 8 + 2 * t;
-                        const int qa = qrow0 + g, qc = qrow0 + g + 8;
-                        const uint32_t ha = attn_hash(p.drop_seed, bh, qa, key, S), hc = attn_hash(p.drop_seed, bh, qc, key, S);
-                        e0 = attn_keep_from(ha, qa, key, p.drop_thresh16) ? e0 * p.drop_scale : 0.f;
-                        e1 = attn_keep_from(ha, qa, key + 1, p.drop_thresh16) ? e1 * p.drop_scale : 0.f;
-                        e2 = attn_keep_from(hc, qc, key, p.drop_thresh16) ? e2 * p.drop_scale : 0.f;
-                        e3 = attn_keep_from(hc, qc, key + 1, p.drop_thresh16) ? e3 * p.drop_scale : 0.f;
+                        const int bit = nt * 8 + 2 * t;
+                        e0 = ((keep_a >> bit) & 1ull) ? e0 * p.drop_scale : 0.f;
+                        e1 = ((keep_a >> (bit + 1)) & 1ull) ? e1 * p.drop_scale : 0.f;
+                        e2 = ((keep_c >> bit) & 1ull) ? e2 * p.drop_scale : 0.f;
+                        e3 = ((keep_c >> (bit + 1)) & 1ull) ? e3 * p.drop_scale : 0.f;
                     }
                     s[nt][0] = p0 * (e0 - d0); s[nt][1] = p1 * (e1 - d0);
                     s[nt][2] = p2 * (e2 - d1); s[nt][3] = p3 * (e3 - d1);
@@ -529,13 +555,17 @@ attn_bwd_dkv_kernel(const AttnParams p, const int nsub) {
             if (p.drop_scale != 0.f) {
                 keepbits = 0;
 #pragma unroll
+                // 16-bit slice of the row masks: bit g = key ka, bit 8+g = key kc (= ka + 8)
+                const unsigned short* kp16 = reinterpret_cast<const unsigned short*>(
+                    p.keep + (static_cast<unsigned long long>(bh) * (nqb * kBlk)) * nqb) + kbk * 4 + warp;
+#pragma unroll
                 for (int nt = 0; nt < 8; ++nt) {
-                    const int q = qb * kBlk + nt * 8 + 2 * t;  // even: (q, q+1) share a hash block
-                    const uint32_t ha = attn_hash(p.drop_seed, bh, q, ka, S), hc = attn_hash(p.drop_seed, bh, q, kc, S);
-                    keepbits |= static_cast<unsigned>(attn_keep_from(ha, q, ka, p.drop_thresh16)) << (nt * 4);
-                    keepbits |= static_cast<unsigned>(attn_keep_from(ha, q + 1, ka, p.drop_thresh16)) << (nt * 4 + 1);
-                    keepbits |= static_cast<unsigned>(attn_keep_from(hc, q, kc, p.drop_thresh16)) << (nt * 4 + 2);
-                    keepbits |= static_cast<unsigned>(attn_keep_from(hc, q + 1, kc, p.drop_thresh16)) << (nt * 4 + 3);
+                    const long long q = qb * kBlk + nt * 8 + 2 * t;
+                    const unsigned w0 = kp16[q * (nqb * 4)], w1 = kp16[(q + 1) * (nqb * 4)];
+                    keepbits |= ((w0 >> g) & 1u) << (nt * 4);
+                    keepbits |= ((w1 >> g) & 1u) << (nt * 4 + 1);
+                    keepbits |= ((w0 >> (8 + g)) & 1u) << (nt * 4 + 2);
+                    keepbits |= ((w1 >> (8 + g)) & 1u) << (nt * 4 + 3);
                 }
             }
             const float ds = p.drop_scale != 0.f ? p.drop_scale : 1.f;
@@ -584,12 +614,14 @@ attn_bwd_dkv_kernel(const AttnParams p, const int nsub) {
 // host
 // ------------------------------------------------------------------------------------------------
 static int fill_params(AttnParams& p, const void* qkv, const float* mask_bias, void* ctx, float* lse,
-                       const void* dctx, void* dqkv, float* drow, int B, int S, int A, int H, float dropout_p,
-                       unsigned long long seed, unsigned stream_id) {
+                       const void* dctx, void* dqkv, float* drow, void* keep, int B, int S, int A, int H,
+                       float dropout_p, unsigned long long seed, unsigned stream_id) {
     VB_REQUIRE(B > 0 && S > 0 && A > 0, "attention: empty problem");
     VB_REQUIRE(H == A * kHd, "attention: head_dim must be 64 (hidden=%d heads=%d)", H, A);
     VB_REQUIRE(A <= 65535 && B <= 65535, "attention: grid too large");
     VB_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "attention: dropout_p out of range");
+    VB_REQUIRE(dropout_p == 0.f || keep != nullptr, "attention: dropout needs the keep-mask buffer (vb_attention_keep_bytes)");
+    p.keep = static_cast<unsigned long long*>(keep);
     p.qkv = static_cast<const bf16*>(qkv);
     p.mask_bias = mask_bias;
     p.ctx = static_cast<bf16*>(ctx);
@@ -611,10 +643,15 @@ static int fill_params(AttnParams& p, const void* qkv, const float* mask_bias, v
     return 0;
 }
 
-int attn_fwd(const void* qkv, const float* mask_bias, void* ctx, float* lse, int B, int S, int A, int H,
+long long attn_keep_bytes(int B, int S, int A) {
+    const long long nkb = (S + kBlk - 1) / kBlk;
+    return static_cast<long long>(B) * A * (nkb * kBlk) * nkb * 8;
+}
+
+int attn_fwd(const void* qkv, const float* mask_bias, void* ctx, float* lse, void* keep, int B, int S, int A, int H,
              float dropout_p, unsigned long long seed, unsigned stream_id, cudaStream_t st) {
     AttnParams p;
-    int rc = fill_params(p, qkv, mask_bias, ctx, lse, nullptr, nullptr, nullptr, B, S, A, H, dropout_p, seed, stream_id);
+    int rc = fill_params(p, qkv, mask_bias, ctx, lse, nullptr, nullptr, nullptr, keep, B, S, A, H, dropout_p, seed, stream_id);
     if (rc) return rc;
     dim3 grid((S + kBlk - 1) / kBlk, A, B);
     const int nsub = static_cast<int>(grid.x) < kMaxSub ? static_cast<int>(grid.x) : kMaxSub;
@@ -634,12 +671,12 @@ int attn_fwd(const void* qkv, const float* mask_bias, void* ctx, float* lse, int
 
 static int g_bwd_minb = 3;
 
-int attn_bwd(const void* qkv, const float* mask_bias, const void* ctx, const float* lse, const void* dctx,
-             void* dqkv, float* drow, int B, int S, int A, int H, float dropout_p, unsigned long long seed,
-             unsigned stream_id, cudaStream_t st) {
+int attn_bwd(const void* qkv, const float* mask_bias, const void* ctx, const float* lse, const void* keep,
+             const void* dctx, void* dqkv, float* drow, int B, int S, int A, int H, float dropout_p,
+             unsigned long long seed, unsigned stream_id, cudaStream_t st) {
     AttnParams p;
-    int rc = fill_params(p, qkv, mask_bias, const_cast<void*>(ctx), const_cast<float*>(lse), dctx, dqkv, drow, B, S,
-                         A, H, dropout_p, seed, stream_id);
+    int rc = fill_params(p, qkv, mask_bias, const_cast<void*>(ctx), const_cast<float*>(lse), dctx, dqkv, drow,
+                         const_cast<void*>(keep), B, S, A, H, dropout_p, seed, stream_id);
     if (rc) return rc;
     static bool configured = false;
     if (!configured) {
@@ -670,16 +707,19 @@ int attn_bwd(const void* qkv, const float* mask_bias, const void* ctx, const flo
 }  // namespace vb
 
 extern "C" {
-int vb_attention_fwd(const void* qkv, const float* mask_bias, void* ctx, float* lse, int32_t batch, int32_t seq,
-                     int32_t heads, int32_t hidden, float dropout_p, uint64_t dropout_seed, uint32_t dropout_stream,
-                     void* stream) {
-    return vb::attn_fwd(qkv, mask_bias, ctx, lse, batch, seq, heads, hidden, dropout_p, dropout_seed, dropout_stream,
-                        static_cast<cudaStream_t>(stream));
+int64_t vb_attention_keep_bytes(int32_t batch, int32_t seq, int32_t heads) {
+    return vb::attn_keep_bytes(batch, seq, heads);
 }
-int vb_attention_bwd(const void* qkv, const float* mask_bias, const void* ctx, const float* lse, const void* dctx,
-                     void* dqkv, float* drow, int32_t batch, int32_t seq, int32_t heads, int32_t hidden,
-                     float dropout_p, uint64_t dropout_seed, uint32_t dropout_stream, void* stream) {
-    return vb::attn_bwd(qkv, mask_bias, ctx, lse, dctx, dqkv, drow, batch, seq, heads, hidden, dropout_p, dropout_seed,
+int vb_attention_fwd(const void* qkv, const float* mask_bias, void* ctx, float* lse, void* keep_mask, int32_t batch,
+                     int32_t seq, int32_t heads, int32_t hidden, float dropout_p, uint64_t dropout_seed,
+                     uint32_t dropout_stream, void* stream) {
+    return vb::attn_fwd(qkv, mask_bias, ctx, lse, keep_mask, batch, seq, heads, hidden, dropout_p, dropout_seed,
                         dropout_stream, static_cast<cudaStream_t>(stream));
+}
+int vb_attention_bwd(const void* qkv, const float* mask_bias, const void* ctx, const float* lse, const void* keep_mask,
+                     const void* dctx, void* dqkv, float* drow, int32_t batch, int32_t seq, int32_t heads,
+                     int32_t hidden, float dropout_p, uint64_t dropout_seed, uint32_t dropout_stream, void* stream) {
+    return vb::attn_bwd(qkv, mask_bias, ctx, lse, keep_mask, dctx, dqkv, drow, batch, seq, heads, hidden, dropout_p,
+                        dropout_seed, dropout_stream, static_cast<cudaStream_t>(stream));
 }
 }

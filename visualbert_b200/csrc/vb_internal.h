@@ -11,11 +11,11 @@ int ln_fwd(const void* x, long long ldx, const float* gamma, const float* beta, 
 int ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
            void* dx_drop, float* dgamma, float* dbeta, float* dbias, int rows, int H, float dropout_p,
            unsigned long long seed, unsigned stream_id, float in_dropout_p, unsigned in_stream_id, cudaStream_t st);
-int attn_fwd(const void* qkv, const float* mask_bias, void* ctx, float* lse, int B, int S, int A, int H,
+int attn_fwd(const void* qkv, const float* mask_bias, void* ctx, float* lse, void* keep, int B, int S, int A, int H,
              float dropout_p, unsigned long long seed, unsigned stream_id, cudaStream_t st);
-int attn_bwd(const void* qkv, const float* mask_bias, const void* ctx, const float* lse, const void* dctx,
-             void* dqkv, float* drow, int B, int S, int A, int H, float dropout_p, unsigned long long seed,
-             unsigned stream_id, cudaStream_t st);
+int attn_bwd(const void* qkv, const float* mask_bias, const void* ctx, const float* lse, const void* keep,
+             const void* dctx, void* dqkv, float* drow, int B, int S, int A, int H, float dropout_p,
+             unsigned long long seed, unsigned stream_id, cudaStream_t st);
 int colsum(const void* x, long long ld, float* out, int M, int N, cudaStream_t st);
 int cast_f32_bf16(const float* src, void* dst, long long n, cudaStream_t st);
 int cast_bf16_f32(const void* src, float* dst, long long n, cudaStream_t st);

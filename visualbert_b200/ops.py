@@ -144,7 +144,9 @@ class _LayerFn(torch.autograd.Function):
             mean1=torch.empty(M, device=dev, dtype=f32), rstd1=torch.empty(M, device=dev, dtype=f32),
             x1=torch.empty(M, H, device=dev, dtype=_BF16), u=torch.empty(M, I, device=dev, dtype=_BF16),
             g=torch.empty(M, I, device=dev, dtype=_BF16), pre2=torch.empty(M, H, device=dev, dtype=_BF16),
-            mean2=torch.empty(M, device=dev, dtype=f32), rstd2=torch.empty(M, device=dev, dtype=f32))
+            mean2=torch.empty(M, device=dev, dtype=f32), rstd2=torch.empty(M, device=dev, dtype=f32),
+            keep_mask=(torch.empty(int(_lib.lib().vb_attention_keep_bytes(B, S, A)), device=dev, dtype=torch.uint8)
+                       if meta["attn_dropout"] > 0 else None))
         y = torch.empty(B, S, H, device=dev, dtype=_BF16)
         d = _lib.LayerDesc(
             batch=B, seq=S, hidden=H, heads=A, inter=I, hidden_dropout=meta["hidden_dropout"],
@@ -153,7 +155,7 @@ class _LayerFn(torch.autograd.Function):
             b_qkv=bqkv.data_ptr(), b_attn_out=ob.data_ptr(), ln1_gamma=g1.data_ptr(), ln1_beta=b1.data_ptr(),
             b_inter=ib.data_ptr(), b_out=db.data_ptr(), ln2_gamma=g2.data_ptr(), ln2_beta=b2.data_ptr(),
             mask_bias=mbias.data_ptr())
-        a = _lib.LayerActs(**{k: t.data_ptr() for k, t in acts.items()})
+        a = _lib.LayerActs(**{k: _ptr(t) for k, t in acts.items()})
         _lib.check(_lib.lib().vb_layer_fwd(ctypes.byref(d), ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(y.data_ptr()),
                                            ctypes.byref(a), _stream()), "vb_layer_fwd")
         ctx.meta = meta
@@ -198,7 +200,7 @@ class _LayerFn(torch.autograd.Function):
             b_qkv=bqkv.data_ptr(), b_attn_out=ob.data_ptr(), ln1_gamma=g1.data_ptr(), ln1_beta=b1.data_ptr(),
             b_inter=ib.data_ptr(), b_out=db.data_ptr(), ln2_gamma=g2.data_ptr(), ln2_beta=b2.data_ptr(),
             mask_bias=mbias.data_ptr())
-        a = _lib.LayerActs(**{k: t.data_ptr() for k, t in acts.items()})
+        a = _lib.LayerActs(**{k: _ptr(t) for k, t in acts.items()})
         dx = torch.empty(B, S, H, device=dev, dtype=_BF16)
         _lib.check(_lib.lib().vb_layer_bwd(ctypes.byref(d), ctypes.c_void_p(x.data_ptr()), ctypes.byref(a),
                                            ctypes.c_void_p(dy.data_ptr()), ctypes.c_void_p(dx.data_ptr()),
