@@ -31,9 +31,12 @@ const char* vb_last_error(void);
 /* number of kernel launches issued by this library on the calling process since load */
 int64_t vb_launch_count(void);
 /* Live profiling: when enabled every launcher brackets its kernels with CUDA events on the launch stream.
- * vb_profile_read synchronises the device and returns, per category (0 GEMM/tcgen05, 1 attention,
- * 2 row-wise HBM-bound kernels, 3 other), the summed kernel time [ms], the algorithmic work (FLOPs for
- * 0-1, bytes for 2-3) and the number of launches since the previous read; arrays of 4. */
+ * vb_profile_read synchronises the device and returns, per category, the summed kernel time [ms], the
+ * algorithmic work (FLOPs for the tensor-core kernels, bytes for the HBM-bound ones) and the number of launches
+ * since the previous read; arrays of VB_PROFILE_CATEGORIES entries:
+ * 0 gemm fwd, 1 gemm dgrad, 2 gemm wgrad (all gemm_tcgen05_kernel), 3 attention fwd, 4 attention dQ,
+ * 5 attention dK/dV, 6 layernorm fwd, 7 layernorm bwd, 8 column sums, 9 embedding, 10 other. */
+#define VB_PROFILE_CATEGORIES 11
 void vb_profile_enable(int on);
 int vb_profile_read(double* ms, double* work, int64_t* launches);
 

@@ -102,7 +102,8 @@ def launch_count():
     return int(lib().vb_launch_count())
 
 
-PROFILE_CATEGORIES = ("gemm_tcgen05", "attention", "rowwise", "other")
+PROFILE_CATEGORIES = ("gemm_fwd", "gemm_dgrad", "gemm_wgrad", "attn_fwd", "attn_dq", "attn_dkv", "ln_fwd", "ln_bwd",
+                      "colsum", "embed", "other")
 
 
 def profile_enable(on=True):
@@ -111,6 +112,7 @@ def profile_enable(on=True):
 
 def profile_read():
     """-> {category: dict(ms, work, launches)} since the previous read (synchronises the device)."""
-    ms = (ctypes.c_double * 4)(); work = (ctypes.c_double * 4)(); n = (ctypes.c_int64 * 4)()
+    k = len(PROFILE_CATEGORIES)
+    ms = (ctypes.c_double * k)(); work = (ctypes.c_double * k)(); n = (ctypes.c_int64 * k)()
     check(lib().vb_profile_read(ms, work, n), "vb_profile_read")
     return {c: dict(ms=ms[i], work=work[i], launches=int(n[i])) for i, c in enumerate(PROFILE_CATEGORIES)}

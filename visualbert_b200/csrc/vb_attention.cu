@@ -58,11 +58,12 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // 64 x 64 bf16 tile: rows row0..row0+63 of a [*, ld] matrix starting at column col0; rows >= nrows -> 0
+template <int NT = 128>
 __device__ __forceinline__ void load_tile(uint32_t tile, const bf16* base, long long ld, int row0, int nrows,
                                           int tid) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int idx = tid + i * 128;
+    for (int i = 0; i < 512 / NT; ++i) {
+        const int idx = tid + i * NT;
         const int r = idx >> 3, c = idx & 7;
         const bool ok = (row0 + r) < nrows;
         const bf16* src = base + static_cast<long long>(ok ? row0 + r : 0) * ld + c * 8;
@@ -130,6 +131,49 @@ __device__ __forceinline__ void gemm_nn(float (&acc)[8][4], const uint32_t (&a)[
                 ldsm_x4_t(tile + swz(row, chunk), b0, b1, b2, b3);
                 mma16816(acc[2 * np], a[ks], b0, b1);
                 mma16816(acc[2 * np + 1], a[ks], b2, b3);
+            }
+        }
+    }
+}
+// MT m-tiles per warp (16*MT rows): every B fragment fetched by ldmatrix feeds 2*MT MMAs
+template <int MT>
+__device__ __forceinline__ void gemm_nt_mt(float (&acc)[MT][8][4], const uint32_t (&a)[MT][4][4], uint32_t tile, int lane,
+                                           int nvalid) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+            if (np * 16 < nvalid) {
+                const int row = np * 16 + (lane & 7) + (lane >> 4) * 8;
+                const int chunk = ks * 2 + ((lane >> 3) & 1);
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4(tile + swz(row, chunk), b0, b1, b2, b3);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    mma16816(acc[mt][2 * np], a[mt][ks], b0, b1);
+                    mma16816(acc[mt][2 * np + 1], a[mt][ks], b2, b3);
+                }
+            }
+        }
+    }
+}
+template <int MT>
+__device__ __forceinline__ void gemm_nn_mt(float (&acc)[MT][8][4], const uint32_t (&a)[MT][4][4], uint32_t tile, int lane,
+                                           int kvalid) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        if (ks * 16 < kvalid) {
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {
+                const int row = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                const int chunk = np * 2 + (lane >> 4);
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4_t(tile + swz(row, chunk), b0, b1, b2, b3);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    mma16816(acc[mt][2 * np], a[mt][ks], b0, b1);
+                    mma16816(acc[mt][2 * np + 1], a[mt][ks], b2, b3);
+                }
             }
         }
     }
@@ -233,8 +277,12 @@ __device__ __forceinline__ void store_acc(bf16* base, long long ld, int row0, in
 // are about to consume.
 constexpr int kMaxSub = 4;
 
-__global__ void __launch_bounds__(128, 3)
+// MT = m16 tiles per warp: 1 -> 4 warps x 16 rows, 2 -> 2 warps x 32 rows (FA2-style: each ldmatrix'd K/V
+// fragment feeds twice as many MMAs and the warp carries twice as many independent accumulators).
+template <int MT, int MINB>
+__global__ void __launch_bounds__(128 / MT, MINB)
 attn_fwd_kernel(const AttnParams p, const int nsub) {
+    constexpr int NT = 128 / MT;
     extern __shared__ __align__(128) uint8_t dsmem[];
     __shared__ float sbias[kMaxSub * kBlk];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -249,24 +297,29 @@ attn_fwd_kernel(const AttnParams p, const int nsub) {
     const int nkb = (S + kBlk - 1) / kBlk;
 
     const float sc2 = p.scale * kLog2e;
-    float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
-    float o[8][4];
-    zero_acc(o);
-    uint32_t qf[4][4];
+    float m[MT][2], l[MT][2];
+    float o[MT][8][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        m[mt][0] = m[mt][1] = -INFINITY;
+        l[mt][0] = l[mt][1] = 0.f;
+        zero_acc(o[mt]);
+    }
+    uint32_t qf[MT][4][4];
     const unsigned bh = static_cast<unsigned>(b * p.A + h);
-    const int qrow0 = qb * kBlk + warp * 16;
-    const bool active = qrow0 < S;  // warps whose 16 query rows are all padding only help with the loads
+    const int qrow0 = qb * kBlk + warp * 16 * MT;
+    const bool active = qrow0 < S;  // warps whose query rows are all padding only help with the loads
 
     for (int kb0 = 0; kb0 < nkb; kb0 += nsub) {
         const int nb = min(nsub, nkb - kb0);
         if (kb0 > 0) __syncthreads();  // previous stage fully consumed
-        if (kb0 == 0) load_tile(sQ, qbase, ld, qb * kBlk, S, tid);
+        if (kb0 == 0) load_tile<NT>(sQ, qbase, ld, qb * kBlk, S, tid);
         for (int j = 0; j < nb; ++j) {
-            load_tile(sK0 + j * kTileBytes, kbase, ld, (kb0 + j) * kBlk, S, tid);
-            load_tile(sV0 + j * kTileBytes, vbase, ld, (kb0 + j) * kBlk, S, tid);
+            load_tile<NT>(sK0 + j * kTileBytes, kbase, ld, (kb0 + j) * kBlk, S, tid);
+            load_tile<NT>(sV0 + j * kTileBytes, vbase, ld, (kb0 + j) * kBlk, S, tid);
             cp_async_commit();
         }
-        for (int i = tid; i < nb * kBlk; i += 128) {
+        for (int i = tid; i < nb * kBlk; i += NT) {
             const int key = kb0 * kBlk + i;
             sbias[i] = key < S ? p.mask_bias[static_cast<long long>(b) * S + key] * kLog2e : -INFINITY;
         }
@@ -274,79 +327,90 @@ attn_fwd_kernel(const AttnParams p, const int nsub) {
             cp_async_wait_dyn(nb - 1 - j);
             __syncthreads();
             if (!active) continue;
-            if (kb0 == 0 && j == 0) load_afrag(qf, sQ, warp * 16, lane);
+            if (kb0 == 0 && j == 0) {
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) load_afrag(qf[mt], sQ, warp * 16 * MT + mt * 16, lane);
+            }
             const int kb = kb0 + j;
             const int kvalid = min(kBlk, S - kb * kBlk);
-            float s[8][4];
-            zero_acc(s);
-            gemm_nt(s, qf, sK0 + j * kTileBytes, lane, kvalid);
-            float mx[2] = {-INFINITY, -INFINITY};
+            float s[MT][8][4];
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                const float b0 = sbias[j * kBlk + nt * 8 + 2 * t], b1 = sbias[j * kBlk + nt * 8 + 2 * t + 1];
-                s[nt][0] = fmaf(s[nt][0], sc2, b0); s[nt][1] = fmaf(s[nt][1], sc2, b1);
-                s[nt][2] = fmaf(s[nt][2], sc2, b0); s[nt][3] = fmaf(s[nt][3], sc2, b1);
-                mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
-                mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
-            }
-            float alpha[2];
+            for (int mt = 0; mt < MT; ++mt) zero_acc(s[mt]);
+            gemm_nt_mt<MT>(s, qf, sK0 + j * kTileBytes, lane, kvalid);
+            uint32_t pf[MT][4][4];
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
-                mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-                const float mn = fmaxf(m[r], mx[r]);
-                alpha[r] = fast_ex2(m[r] - mn);
-                m[r] = mn;
-            }
-            float rs[2] = {0.f, 0.f};
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                s[nt][0] = fast_ex2(s[nt][0] - m[0]); s[nt][1] = fast_ex2(s[nt][1] - m[0]);
-                s[nt][2] = fast_ex2(s[nt][2] - m[1]); s[nt][3] = fast_ex2(s[nt][3] - m[1]);
-                rs[0] += s[nt][0] + s[nt][1];
-                rs[1] += s[nt][2] + s[nt][3];
-            }
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
-                rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
-                l[r] = l[r] * alpha[r] + rs[r];
-            }
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                o[nt][0] *= alpha[0]; o[nt][1] *= alpha[0];
-                o[nt][2] *= alpha[1]; o[nt][3] *= alpha[1];
-            }
-            if (p.drop_scale != 0.f) {
-                const int qa = qrow0 + g, qc = qrow0 + g + 8;
-                const uint32_t ka_bits = attn_keep16(p.drop_seed, bh, qa, kb, t, S, p.drop_thresh16);
-                const uint32_t kc_bits = attn_keep16(p.drop_seed, bh, qc, kb, t, S, p.drop_thresh16);
+            for (int mt = 0; mt < MT; ++mt) {
+                float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
                 for (int nt = 0; nt < 8; ++nt) {
-                    s[nt][0] = ((ka_bits >> (2 * nt)) & 1u) ? s[nt][0] * p.drop_scale : 0.f;
-                    s[nt][1] = ((ka_bits >> (2 * nt + 1)) & 1u) ? s[nt][1] * p.drop_scale : 0.f;
-                    s[nt][2] = ((kc_bits >> (2 * nt)) & 1u) ? s[nt][2] * p.drop_scale : 0.f;
-                    s[nt][3] = ((kc_bits >> (2 * nt + 1)) & 1u) ? s[nt][3] * p.drop_scale : 0.f;
+                    const float b0 = sbias[j * kBlk + nt * 8 + 2 * t], b1 = sbias[j * kBlk + nt * 8 + 2 * t + 1];
+                    s[mt][nt][0] = fmaf(s[mt][nt][0], sc2, b0); s[mt][nt][1] = fmaf(s[mt][nt][1], sc2, b1);
+                    s[mt][nt][2] = fmaf(s[mt][nt][2], sc2, b0); s[mt][nt][3] = fmaf(s[mt][nt][3], sc2, b1);
+                    mx[0] = fmaxf(mx[0], fmaxf(s[mt][nt][0], s[mt][nt][1]));
+                    mx[1] = fmaxf(mx[1], fmaxf(s[mt][nt][2], s[mt][nt][3]));
                 }
-                const unsigned long long ma = quad_mask64(ka_bits, t), mc = quad_mask64(kc_bits, t);
-                if (t == 0) {  // rows are padded to nkb*64 in the mask buffer: no bounds check needed
-                    unsigned long long* kp = p.keep + (static_cast<unsigned long long>(bh) * (nkb * kBlk)) * nkb;
-                    kp[static_cast<long long>(qa) * nkb + kb] = ma;
-                    kp[static_cast<long long>(qc) * nkb + kb] = mc;
+                float alpha[2];
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+                    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+                    const float mn = fmaxf(m[mt][r], mx[r]);
+                    alpha[r] = fast_ex2(m[mt][r] - mn);
+                    m[mt][r] = mn;
                 }
+                float rs[2] = {0.f, 0.f};
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    s[mt][nt][0] = fast_ex2(s[mt][nt][0] - m[mt][0]); s[mt][nt][1] = fast_ex2(s[mt][nt][1] - m[mt][0]);
+                    s[mt][nt][2] = fast_ex2(s[mt][nt][2] - m[mt][1]); s[mt][nt][3] = fast_ex2(s[mt][nt][3] - m[mt][1]);
+                    rs[0] += s[mt][nt][0] + s[mt][nt][1];
+                    rs[1] += s[mt][nt][2] + s[mt][nt][3];
+                }
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
+                    rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
+                    l[mt][r] = l[mt][r] * alpha[r] + rs[r];
+                }
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    o[mt][nt][0] *= alpha[0]; o[mt][nt][1] *= alpha[0];
+                    o[mt][nt][2] *= alpha[1]; o[mt][nt][3] *= alpha[1];
+                }
+                if (p.drop_scale != 0.f) {
+                    const int qa = qrow0 + mt * 16 + g, qc = qa + 8;
+                    const uint32_t ka_bits = attn_keep16(p.drop_seed, bh, qa, kb, t, S, p.drop_thresh16);
+                    const uint32_t kc_bits = attn_keep16(p.drop_seed, bh, qc, kb, t, S, p.drop_thresh16);
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt) {
+                        s[mt][nt][0] = ((ka_bits >> (2 * nt)) & 1u) ? s[mt][nt][0] * p.drop_scale : 0.f;
+                        s[mt][nt][1] = ((ka_bits >> (2 * nt + 1)) & 1u) ? s[mt][nt][1] * p.drop_scale : 0.f;
+                        s[mt][nt][2] = ((kc_bits >> (2 * nt)) & 1u) ? s[mt][nt][2] * p.drop_scale : 0.f;
+                        s[mt][nt][3] = ((kc_bits >> (2 * nt + 1)) & 1u) ? s[mt][nt][3] * p.drop_scale : 0.f;
+                    }
+                    const unsigned long long ma = quad_mask64(ka_bits, t), mc = quad_mask64(kc_bits, t);
+                    if (t == 0) {  // rows are padded to nkb*64 in the mask buffer: no bounds check needed
+                        unsigned long long* kp = p.keep + (static_cast<unsigned long long>(bh) * (nkb * kBlk)) * nkb;
+                        kp[static_cast<long long>(qa) * nkb + kb] = ma;
+                        kp[static_cast<long long>(qc) * nkb + kb] = mc;
+                    }
+                }
+                acc_to_afrag(pf[mt], s[mt]);
             }
-            uint32_t pf[4][4];
-            acc_to_afrag(pf, s);
-            gemm_nn(o, pf, sV0 + j * kTileBytes, lane, kvalid);
+            gemm_nn_mt<MT>(o, pf, sV0 + j * kTileBytes, lane, kvalid);
         }
     }
     if (!active) return;
-    const float inv0 = 1.f / l[0], inv1 = 1.f / l[1];
-    store_acc(p.ctx + static_cast<long long>(b) * S * p.H + h * kHd, p.H, qrow0, S, o, lane, inv0, inv1);
-    if (t == 0 && p.lse != nullptr) {
-        float* lse = p.lse + (static_cast<long long>(b) * p.A + h) * S;
-        if (qrow0 + g < S) lse[qrow0 + g] = (m[0] + log2f(l[0])) * 0.6931471805599453f;
-        if (qrow0 + g + 8 < S) lse[qrow0 + g + 8] = (m[1] + log2f(l[1])) * 0.6931471805599453f;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        const int r0 = qrow0 + mt * 16;
+        const float inv0 = 1.f / l[mt][0], inv1 = 1.f / l[mt][1];
+        store_acc(p.ctx + static_cast<long long>(b) * S * p.H + h * kHd, p.H, r0, S, o[mt], lane, inv0, inv1);
+        if (t == 0 && p.lse != nullptr) {
+            float* lse = p.lse + (static_cast<long long>(b) * p.A + h) * S;
+            if (r0 + g < S) lse[r0 + g] = (m[mt][0] + log2f(l[mt][0])) * 0.6931471805599453f;
+            if (r0 + g + 8 < S) lse[r0 + g + 8] = (m[mt][1] + log2f(l[mt][1])) * 0.6931471805599453f;
+        }
     }
 }
 
@@ -656,14 +720,26 @@ int attn_fwd(const void* qkv, const float* mask_bias, void* ctx, float* lse, voi
     dim3 grid((S + kBlk - 1) / kBlk, A, B);
     const int nsub = static_cast<int>(grid.x) < kMaxSub ? static_cast<int>(grid.x) : kMaxSub;
     const int smem = (1 + 2 * nsub) * kTileBytes;
-    static bool configured = false;
-    if (!configured) {
-        VB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 + 2 * kMaxSub) * kTileBytes));
-        configured = true;
+    static int variant = -1;  // tuning knob VB_ATTN_FWD = "<MT><MINB>": 13 14 23 24 25
+    if (variant < 0) {
+        const int maxb = (1 + 2 * kMaxSub) * kTileBytes;
+        VB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+        VB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+        VB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+        VB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+        VB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+        const char* e = getenv("VB_ATTN_FWD");
+        variant = e ? atoi(e) : 13;
     }
     {
-        ProfScope ps(st, PROF_ATTN, 4.0 * B * A * S * S * kHd, 1);
-        attn_fwd_kernel<<<grid, 128, smem, st>>>(p, nsub);
+        ProfScope ps(st, PROF_ATTN_FWD, 4.0 * B * A * S * S * kHd, 1);
+        switch (variant) {
+            case 14: attn_fwd_kernel<1, 4><<<grid, 128, smem, st>>>(p, nsub); break;
+            case 23: attn_fwd_kernel<2, 3><<<grid, 64, smem, st>>>(p, nsub); break;
+            case 24: attn_fwd_kernel<2, 4><<<grid, 64, smem, st>>>(p, nsub); break;
+            case 25: attn_fwd_kernel<2, 5><<<grid, 64, smem, st>>>(p, nsub); break;
+            default: attn_fwd_kernel<1, 3><<<grid, 128, smem, st>>>(p, nsub); break;
+        }
     }
     VB_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -690,15 +766,15 @@ int attn_bwd(const void* qkv, const float* mask_bias, const void* ctx, const flo
     }
     dim3 grid((S + kBlk - 1) / kBlk, A, B);
     const int nsub = static_cast<int>(grid.x) < kMaxSub ? static_cast<int>(grid.x) : kMaxSub;
+    {   // algorithmic work of the backward = 2x forward (recompute not credited), split evenly over the two kernels
+        ProfScope ps(st, PROF_ATTN_DQ, 4.0 * B * A * S * S * kHd, 1);
+        if (g_bwd_minb == 2) attn_bwd_dq_kernel<2><<<grid, 128, (3 + 2 * nsub) * kTileBytes, st>>>(p, nsub);
+        else attn_bwd_dq_kernel<3><<<grid, 128, (3 + 2 * nsub) * kTileBytes, st>>>(p, nsub);
+    }
     {
-        ProfScope ps(st, PROF_ATTN, 8.0 * B * A * S * S * kHd, 2);  // algorithmic: 2x forward
-        if (g_bwd_minb == 2) {
-            attn_bwd_dq_kernel<2><<<grid, 128, (3 + 2 * nsub) * kTileBytes, st>>>(p, nsub);
-            attn_bwd_dkv_kernel<2><<<grid, 128, (2 + 2 * nsub) * kTileBytes, st>>>(p, nsub);
-        } else {
-            attn_bwd_dq_kernel<3><<<grid, 128, (3 + 2 * nsub) * kTileBytes, st>>>(p, nsub);
-            attn_bwd_dkv_kernel<3><<<grid, 128, (2 + 2 * nsub) * kTileBytes, st>>>(p, nsub);
-        }
+        ProfScope ps(st, PROF_ATTN_DKV, 4.0 * B * A * S * S * kHd, 1);
+        if (g_bwd_minb == 2) attn_bwd_dkv_kernel<2><<<grid, 128, (2 + 2 * nsub) * kTileBytes, st>>>(p, nsub);
+        else attn_bwd_dkv_kernel<3><<<grid, 128, (2 + 2 * nsub) * kTileBytes, st>>>(p, nsub);
     }
     VB_CHECK_CUDA(cudaGetLastError());
     return 0;

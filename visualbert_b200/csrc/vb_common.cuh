@@ -22,7 +22,8 @@ int num_sms();
 
 // Optional live profiling (vb_profile_enable): every launcher brackets its kernels with CUDA events on
 // the launch stream and tags them with a category and the algorithmic work (FLOPs or bytes) of the call.
-enum { PROF_GEMM = 0, PROF_ATTN = 1, PROF_ROWWISE = 2, PROF_OTHER = 3, PROF_NCAT = 4 };
+enum { PROF_GEMM_FWD = 0, PROF_GEMM_DGRAD = 1, PROF_GEMM_WGRAD = 2, PROF_ATTN_FWD = 3, PROF_ATTN_DQ = 4, PROF_ATTN_DKV = 5,
+       PROF_LN_FWD = 6, PROF_LN_BWD = 7, PROF_COLSUM = 8, PROF_EMBED = 9, PROF_OTHER = 10, PROF_NCAT = 11 };
 struct ProfScope {
     ProfScope(cudaStream_t st, int cat, double work, int launches);
     ~ProfScope();

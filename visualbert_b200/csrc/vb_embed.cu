@@ -228,7 +228,7 @@ int embed_fwd(const EmbedParams& p, cudaStream_t st) {
     const long long rows = static_cast<long long>(p.B) * (p.T + p.V);
     const int grid = static_cast<int>((rows + kEmbWarps - 1) / kEmbWarps);
     const int nc = (p.H / 8 + 31) / 32;
-    ProfScope ps(st, PROF_ROWWISE, 8.0 * rows * p.H, 1);
+    ProfScope ps(st, PROF_EMBED, 8.0 * rows * p.H, 1);
     switch (nc) {
         case 1: embed_fwd_kernel<1><<<grid, kEmbWarps * 32, 0, st>>>(p); break;
         case 2: embed_fwd_kernel<2><<<grid, kEmbWarps * 32, 0, st>>>(p); break;
@@ -248,7 +248,7 @@ int embed_bwd(const EmbedBwdParams& p, cudaStream_t st) {
     const size_t smem = static_cast<size_t>(2 * p.n_types + 1) * p.H * sizeof(float);
     VB_REQUIRE(smem <= 48 * 1024, "embed backward: type_vocab_size * hidden too large for shared memory");
     {
-        ProfScope ps(st, PROF_ROWWISE, 6.0 * rows * p.H, 1);
+        ProfScope ps(st, PROF_EMBED, 6.0 * rows * p.H, 1);
         embed_bwd_kernel<<<grid, kEmbWarps * 32, smem, st>>>(p);
     }
     VB_CHECK_CUDA(cudaGetLastError());
@@ -300,7 +300,7 @@ int colsum(const void* x, long long ld, float* out, int M, int N, cudaStream_t s
     if (gy < 1) gy = 1;
     if (gy > (M + 7) / 8) gy = (M + 7) / 8;
     {
-        ProfScope ps(st, PROF_ROWWISE, 2.0 * M * N, 1);
+        ProfScope ps(st, PROF_COLSUM, 2.0 * M * N, 1);
         colsum_kernel<<<dim3(gx, gy), dim3(32, 8), 0, st>>>(static_cast<const bf16*>(x), ld, out, M, N);
     }
     VB_CHECK_CUDA(cudaGetLastError());

@@ -445,7 +445,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
     const int tiles = m_blocks * n_blocks * p.splits;
     const int grid = tiles < num_sms() ? tiles : num_sms();
     {
-        ProfScope ps(st, PROF_GEMM, 2.0 * p.M * p.N * p.K, 1);
+        ProfScope ps(st, OUT_F32 ? PROF_GEMM_WGRAD : (B_MN ? PROF_GEMM_DGRAD : PROF_GEMM_FWD), 2.0 * p.M * p.N * p.K, 1);
         kern<<<grid, kThreads, C::SMEM_BYTES, st>>>(ta, tb, p);
     }
     VB_CHECK_CUDA(cudaGetLastError());

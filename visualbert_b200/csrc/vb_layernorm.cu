@@ -216,7 +216,7 @@ int ln_fwd(const void* x, long long ldx, const float* gamma, const float* beta, 
     const int grid = (rows + kLnWarps - 1) / kLnWarps;
     const bf16* xb = static_cast<const bf16*>(x);
     bf16* yb = static_cast<bf16*>(y);
-    ProfScope ps(st, PROF_ROWWISE, 4.0 * rows * H, 1);  // bytes: read + write bf16
+    ProfScope ps(st, PROF_LN_FWD, 4.0 * rows * H, 1);  // bytes: read + write bf16
 #define VB_LN_FWD(NC) ln_fwd_kernel<NC><<<grid, kLnWarps * 32, 0, st>>>(xb, ldx, gamma, beta, yb, ldy, mean, rstd, rows, H, eps)
     switch (nc) {
         case 1: VB_LN_FWD(1); break;
@@ -253,7 +253,7 @@ int ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, 
         VB_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         configured = true;
     }
-    ProfScope ps(st, PROF_ROWWISE, (dx_drop ? 8.0 : 6.0) * rows * H, 1);
+    ProfScope ps(st, PROF_LN_BWD, (dx_drop ? 8.0 : 6.0) * rows * H, 1);
 #define VB_LN_BWD(NC)                                                                                        \
     ln_bwd_kernel<NC><<<grid, kLnWarps * 32, smem, st>>>(                                                    \
         static_cast<const bf16*>(dy), static_cast<const bf16*>(x), mean, rstd, gamma, static_cast<bf16*>(dx), \
