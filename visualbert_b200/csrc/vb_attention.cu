@@ -475,7 +475,15 @@ int attn_fwd(const void* qkv, const float* mask_bias, void* ctx, float* lse, voi
     int rc = fill_params(p, qkv, mask_bias, ctx, lse, nullptr, nullptr, nullptr, keep, B, S, A, H, dropout_p, seed, stream_id);
     if (rc) return rc;
     dim3 grid((S + kBlk - 1) / kBlk, A, B);
-    if (static_cast<int>(grid.x) <= kMaxSub && !staged_only()) return attn_fwd_head(p, static_cast<int>(grid.x), st);
+    // implementation choice: tcgen05 kernel (default when it applies) > whole-head mma.sync > staged mma.sync;
+    // VB_ATTN_FWD_IMPL = tc | head | staged overrides (testing / tuning)
+    static int impl = -1;
+    if (impl < 0) {
+        const char* e = getenv("VB_ATTN_FWD_IMPL");
+        impl = e == nullptr ? 0 : (e[0] == 'h' ? 1 : (e[0] == 's' ? 2 : 0));
+    }
+    if (impl == 0 && !staged_only() && attn_fwd_tc_supported(p)) return attn_fwd_tc(p, st);
+    if (impl <= 1 && static_cast<int>(grid.x) <= kMaxSub && !staged_only()) return attn_fwd_head(p, static_cast<int>(grid.x), st);
     const int nsub = static_cast<int>(grid.x) < kMaxSub ? static_cast<int>(grid.x) : kMaxSub;
     const int smem = (1 + 2 * nsub) * kTileBytes;
     static bool configured = false;

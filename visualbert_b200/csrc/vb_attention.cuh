@@ -261,5 +261,8 @@ constexpr int kMaxSub = 4;  // 64-row tiles per resident stage
 // whole-head persistent kernels (vb_attention_head.cu); nkb = ceil(S / 64) <= kMaxSub
 int attn_fwd_head(const AttnParams& p, int nkb, cudaStream_t st);
 int attn_bwd_head(const AttnParams& p, int nkb, cudaStream_t st);
+// tcgen05 / TMEM / TMA forward (vb_attention_tc.cu), seq <= 256
+bool attn_fwd_tc_supported(const AttnParams& p);
+int attn_fwd_tc(const AttnParams& p, cudaStream_t st);
 
 }  // namespace vb

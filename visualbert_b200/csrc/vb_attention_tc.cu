@@ -1,0 +1,360 @@
+// vb_attention_tc.cu — attention forward on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), seq <= 256.
+//
+// One persistent CTA per SM walks over work items (batch b, head h, 128-query tile qt):
+//   warp 0      TMA producer: Q tile [128 x 64], K [Npad x 64], V [Npad x 64] of the head (3-D tensor map over
+//               qkv[B][S][3H], so rows >= S are zero-filled), 2-stage mbarrier ring
+//   warp 1      MMA issuer:   S = Q K^T   tcgen05.mma 128 x Npad x 16, 4 k-steps, accumulator in TMEM (double-buffered,
+//                                          so QK^T of item i+1 runs under the softmax of item i)
+//                             O = P V     tcgen05.mma 128 x 64 x 16, Npad/16 k-steps, P read from shared memory
+//                                          (K-major, 128B-swizzled A tile written by the softmax warps), V MN-major
+//   warp 2      TMEM allocator
+//   warps 4-7   softmax + epilogue: one thread per query row (TMEM lane): row max and exp2 straight from TMEM
+//               (two passes, no online rescaling needed because the whole key range is in TMEM), attention dropout
+//               (keep-mask drawn here and stored packed for the backward), P -> bf16 -> swizzled smem tile,
+//               then O * 1/l -> bf16 -> one contiguous 128-byte row store per thread, LSE for the backward.
+//
+// Same math as reference modeling.py:241-256 (scale, additive mask, softmax, dropout, P V, head merge).
+#include "vb_attention.cuh"
+
+namespace vb {
+
+namespace {
+
+constexpr int kQRows = 128;            // query rows per work item (UMMA M)
+constexpr int kThreadsTc = 256;
+constexpr int kSoftmaxThreads = 128;
+
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+// SWIZZLE_128B UMMA shared-memory descriptor (see vb_gemm.cu)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;
+    d |= 2ull << 61;
+    return d;
+}
+__device__ __forceinline__ uint32_t idesc_bf16(int m, int n, bool a_mn, bool b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn) << 15) | (static_cast<uint32_t>(b_mn) << 16) |
+           (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+struct TcLayout {  // shared-memory carve-up (bytes), all tile bases 1 KB aligned
+    int kv_bytes;      // Npad * 128 rounded up to 1 KB
+    int stage_bytes;   // Q + K + V
+    int nstage;
+    int p_off, p_bytes;
+    int bias_off;      // fp32 [2][256]
+    int bar_off;
+    int tmem_ptr_off;
+    int total;
+};
+__host__ __device__ inline TcLayout tc_layout(int npad, int nstage) {
+    TcLayout L;
+    L.kv_bytes = ((npad * 128 + 1023) / 1024) * 1024;
+    L.stage_bytes = kQRows * 128 + 2 * L.kv_bytes;
+    L.nstage = nstage;
+    L.p_off = nstage * L.stage_bytes;
+    L.p_bytes = ((npad + 63) / 64) * kQRows * 128;
+    L.bias_off = L.p_off + L.p_bytes;
+    L.bar_off = L.bias_off + 2 * 256 * 4;
+    L.tmem_ptr_off = L.bar_off + 16 * 8;
+    L.total = L.tmem_ptr_off + 16 + 1024;
+    return L;
+}
+
+struct TcParams {
+    AttnParams a;
+    int npad;      // keys padded to a multiple of 16
+    int nq;        // query tiles per head
+    int nkb;       // ceil(S / 64)
+    int nstage;    // input stages (2 if they fit)
+    int nsbuf;     // TMEM score buffers (2 if they fit)
+};
+
+__global__ void __launch_bounds__(kThreadsTc, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const TcParams tp) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw);
+    const AttnParams& p = tp.a;
+    const TcLayout L = tc_layout(tp.npad, tp.nstage);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = p.S, npad = tp.npad;
+
+    auto q_tile = [&](int s) { return base + s * L.stage_bytes; };
+    auto k_tile = [&](int s) { return base + s * L.stage_bytes + kQRows * 128; };
+    auto v_tile = [&](int s) { return base + s * L.stage_bytes + kQRows * 128 + L.kv_bytes; };
+    const uint32_t p_tile = base + L.p_off;
+    auto bar = [&](int i) { return base + L.bar_off + 8 * i; };
+    // barrier indices
+    enum { FULL0 = 0, EMPTY0 = 2, SFULL0 = 4, SEMPTY0 = 6, PFULL = 8, OFULL = 9, OEMPTY = 10 };
+    volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + L.tmem_ptr_off);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmKV);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar(FULL0 + s), 1);
+            mbar_init(bar(EMPTY0 + s), 1);
+            mbar_init(bar(SFULL0 + s), 1);
+            mbar_init(bar(SEMPTY0 + s), kSoftmaxThreads);
+        }
+        mbar_init(bar(PFULL), kSoftmaxThreads);
+        mbar_init(bar(OFULL), 1);
+        mbar_init(bar(OEMPTY), kSoftmaxThreads);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(base + L.tmem_ptr_off, 512);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_o = tmem_base + 448;                              // O accumulator: columns 448..511
+    auto tmem_s = [&](int sb) { return tmem_base + (sb ? 224u : 0u); };   // score buffers at 0 and 224
+
+    const int total = p.B * p.A * tp.nq;
+    const int n_local = (total - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    auto decode = [&](int li, int& b, int& h, int& qt) {
+        const int item = blockIdx.x + li * gridDim.x;
+        qt = item % tp.nq;
+        const int bh = item / tp.nq;
+        h = bh % p.A;
+        b = bh / p.A;
+    };
+    const uint32_t stage_tx = static_cast<uint32_t>(kQRows * 128 + 2 * npad * 128);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------- TMA producer ----------------
+            for (int li = 0; li < n_local; ++li) {
+                int b, h, qt;
+                decode(li, b, h, qt);
+                const int s = li % tp.nstage;
+                const uint32_t ph = (li / tp.nstage) & 1;
+                mbar_wait(bar(EMPTY0 + s), ph ^ 1u);
+                mbar_arrive_expect_tx(bar(FULL0 + s), stage_tx);
+                tma_load_3d(q_tile(s), &tmQ, bar(FULL0 + s), h * kHd, qt * kQRows, b);
+                tma_load_3d(k_tile(s), &tmKV, bar(FULL0 + s), p.H + h * kHd, 0, b);
+                tma_load_3d(v_tile(s), &tmKV, bar(FULL0 + s), 2 * p.H + h * kHd, 0, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---------------- MMA issuer ----------------
+            const uint32_t idesc_qk = idesc_bf16(kQRows, npad, false, false);
+            const uint32_t idesc_pv = idesc_bf16(kQRows, kHd, false, true);
+            auto do_qk = [&](int j) {
+                const int s = j % tp.nstage, sb = j % tp.nsbuf;
+                mbar_wait(bar(FULL0 + s), (j / tp.nstage) & 1);
+                mbar_wait(bar(SEMPTY0 + sb), ((j / tp.nsbuf) & 1) ^ 1u);
+                tcgen05_fence_after();
+#pragma unroll
+                for (int k = 0; k < kHd / 16; ++k) {
+                    const uint64_t ad = smem_desc_sw128(q_tile(s) + k * 32, 0, 1024);
+                    const uint64_t bd = smem_desc_sw128(k_tile(s) + k * 32, 0, 1024);
+                    umma_bf16(tmem_s(sb), ad, bd, idesc_qk, k > 0 ? 1u : 0u);
+                }
+                umma_commit(bar(SFULL0 + sb));
+            };
+            if (n_local > 0) do_qk(0);
+            for (int li = 0; li < n_local; ++li) {
+                if (li + 1 < n_local && tp.nsbuf == 2 && tp.nstage == 2) do_qk(li + 1);  // under the softmax of item li
+                const int s = li % tp.nstage;
+                mbar_wait(bar(PFULL), li & 1);
+                mbar_wait(bar(OEMPTY), (li & 1) ^ 1u);
+                tcgen05_fence_after();
+                const int ksteps = npad / 16;
+                for (int k = 0; k < ksteps; ++k) {
+                    // P: K-major A, 64-key atoms of [128 rows x 128 B]; V: MN-major B, [keys x 128 B], 16 key rows per step
+                    const uint64_t ad = smem_desc_sw128(p_tile + (k >> 2) * (kQRows * 128) + (k & 3) * 32, 0, 1024);
+                    const uint64_t bd = smem_desc_sw128(v_tile(s) + k * 2048, 0, 1024);
+                    umma_bf16(tmem_o, ad, bd, idesc_pv, k > 0 ? 1u : 0u);
+                }
+                umma_commit(bar(OFULL));
+                umma_commit(bar(EMPTY0 + s));
+                if (li + 1 < n_local && !(tp.nsbuf == 2 && tp.nstage == 2)) do_qk(li + 1);
+            }
+        }
+    } else if (warp >= 4) {
+        // ---------------- softmax + epilogue: one thread per query row ----------------
+        const int q4 = warp & 3;
+        const int r = q4 * 32 + lane;            // row inside the 128-row tile == TMEM lane
+        const int st = threadIdx.x - 128;        // 0..127
+        const uint32_t lane_sel = static_cast<uint32_t>(q4 * 32) << 16;
+        float* sbias_all = reinterpret_cast<float*>(smem + L.bias_off);
+        const float sc2 = p.scale * kLog2e;
+        const int nchunk = npad / 16;
+        for (int li = 0; li < n_local; ++li) {
+            int b, h, qt;
+            decode(li, b, h, qt);
+            const int sb = li % tp.nsbuf;
+            const unsigned bh = static_cast<unsigned>(b * p.A + h);
+            float* sbias = sbias_all + (li & 1) * 256;
+            for (int i = st; i < npad; i += kSoftmaxThreads)
+                sbias[i] = i < S ? p.mask_bias[static_cast<long long>(b) * S + i] * kLog2e : -INFINITY;
+            named_bar_sync(2, kSoftmaxThreads);
+            mbar_wait(bar(SFULL0 + sb), (li / tp.nsbuf) & 1);
+            tcgen05_fence_after();
+            const uint32_t ts = tmem_s(sb) + lane_sel;
+            // pass 1: row maximum of the scaled, masked scores
+            float m = -INFINITY;
+            for (int c = 0; c < nchunk; ++c) {
+                uint32_t v[16];
+                tmem_ld_32x32b_x16(ts + c * 16, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) m = fmaxf(m, fmaf(__uint_as_float(v[i]), sc2, sbias[c * 16 + i]));
+            }
+            // pass 2: probabilities, row sum, dropout, bf16 P tile in shared memory
+            const int q = qt * kQRows + r;       // query index inside the head
+            float lsum = 0.f;
+            unsigned long long keepw = 0;        // keep bits of the current 64-key block
+            for (int c = 0; c < nchunk; ++c) {
+                uint32_t v[16];
+                tmem_ld_32x32b_x16(ts + c * 16, v);
+                tmem_ld_wait();
+                float pr[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    pr[i] = fast_ex2(fmaf(__uint_as_float(v[i]), sc2, sbias[c * 16 + i]) - m);
+                    lsum += pr[i];
+                }
+                if (p.drop_scale != 0.f) {
+                    uint32_t bits = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {  // one hash -> 4 x 8 random bits -> 4 keys
+                        const uint32_t hsh = mix32(((((bh * static_cast<unsigned>(S) + static_cast<unsigned>(q)) << 6) + c * 4 + j)) ^ p.drop_seed);
+                        bits |= static_cast<uint32_t>((hsh & 0xffu) >= p.drop_thresh16) << (4 * j);
+                        bits |= static_cast<uint32_t>(((hsh >> 8) & 0xffu) >= p.drop_thresh16) << (4 * j + 1);
+                        bits |= static_cast<uint32_t>(((hsh >> 16) & 0xffu) >= p.drop_thresh16) << (4 * j + 2);
+                        bits |= static_cast<uint32_t>((hsh >> 24) >= p.drop_thresh16) << (4 * j + 3);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) pr[i] = ((bits >> i) & 1u) ? pr[i] * p.drop_scale : 0.f;
+                    keepw |= static_cast<unsigned long long>(bits) << ((c & 3) * 16);
+                    if ((c & 3) == 3 || c == nchunk - 1) {
+                        if (q < tp.nkb * kBlk)
+                            p.keep[(static_cast<unsigned long long>(bh) * (tp.nkb * kBlk) + q) * tp.nkb + (c >> 2)] = keepw;
+                        keepw = 0;
+                    }
+                }
+                // 16 keys = two 16-byte chunks of row r in the 64-key atom (c / 4)
+                const uint32_t atom = p_tile + (c >> 2) * (kQRows * 128) + r * 128;
+                const int ch0 = (c & 3) * 2;
+                uint4 w0, w1;
+                w0.x = pack_bf16x2(pr[0], pr[1]); w0.y = pack_bf16x2(pr[2], pr[3]);
+                w0.z = pack_bf16x2(pr[4], pr[5]); w0.w = pack_bf16x2(pr[6], pr[7]);
+                w1.x = pack_bf16x2(pr[8], pr[9]); w1.y = pack_bf16x2(pr[10], pr[11]);
+                w1.z = pack_bf16x2(pr[12], pr[13]); w1.w = pack_bf16x2(pr[14], pr[15]);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(atom + ((ch0 ^ (r & 7)) << 4)), "r"(w0.x), "r"(w0.y), "r"(w0.z), "r"(w0.w) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(atom + (((ch0 + 1) ^ (r & 7)) << 4)), "r"(w1.x), "r"(w1.y), "r"(w1.z), "r"(w1.w) : "memory");
+            }
+            tcgen05_fence_before();
+            mbar_arrive(bar(SEMPTY0 + sb));     // scores consumed: the next QK^T may overwrite this TMEM buffer
+            fence_proxy_async_smem();            // P (generic-proxy stores) -> visible to the tensor core (async proxy)
+            mbar_arrive(bar(PFULL));
+            // epilogue: O row * 1/l -> bf16 -> 128 contiguous bytes
+            mbar_wait(bar(OFULL), li & 1);
+            tcgen05_fence_after();
+            uint32_t o[4][16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x16(tmem_o + lane_sel + c * 16, o[c]);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            mbar_arrive(bar(OEMPTY));
+            if (q < S) {
+                const float inv = 1.f / lsum;
+                bf16* dst = p.ctx + (static_cast<long long>(b) * S + q) * p.H + h * kHd;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {  // 16 columns -> 16 bf16 = one 32-byte store
+                    uint32_t w[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        w[i] = pack_bf16x2(__uint_as_float(o[c][2 * i]) * inv, __uint_as_float(o[c][2 * i + 1]) * inv);
+                    stg_v8(dst + c * 16, w);
+                }
+                if (p.lse != nullptr)
+                    p.lse[(static_cast<long long>(b) * p.A + h) * S + q] = (m + log2f(lsum)) * 0.6931471805599453f;
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_tmap_3d(CUtensorMap* m, const void* ptr, int S, int B, int ld, int box_rows) {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    VB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled unavailable");
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(ld), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(B)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(S) * ld * 2};
+    cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", static_cast<int>(r));
+    return 0;
+}
+
+}  // namespace
+
+bool attn_fwd_tc_supported(const AttnParams& p) { return p.S <= 256 && p.S >= 1 && (p.H * 3) % 8 == 0; }
+
+int attn_fwd_tc(const AttnParams& p, cudaStream_t st) {
+    TcParams tp;
+    tp.a = p;
+    tp.npad = ((p.S + 15) / 16) * 16;
+    tp.nq = (p.S + kQRows - 1) / kQRows;
+    tp.nkb = (p.S + kBlk - 1) / kBlk;
+    tp.nsbuf = tp.npad <= 224 ? 2 : 1;
+    tp.nstage = tc_layout(tp.npad, 2).total <= 227 * 1024 ? 2 : 1;
+    const TcLayout L = tc_layout(tp.npad, tp.nstage);
+    VB_REQUIRE(L.total <= 227 * 1024, "attention (tcgen05): shared memory %d bytes exceeds the limit", L.total);
+    CUtensorMap tq, tkv;
+    int rc = make_tmap_3d(&tq, p.qkv, p.S, p.B, 3 * p.H, kQRows);
+    if (rc) return rc;
+    rc = make_tmap_3d(&tkv, p.qkv, p.S, p.B, 3 * p.H, tp.npad);
+    if (rc) return rc;
+    static int configured = 0;
+    if (configured < L.total) {
+        VB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        configured = L.total;
+    }
+    const int total = p.B * p.A * tp.nq;
+    const int grid = total < num_sms() ? total : num_sms();
+    {
+        ProfScope ps(st, PROF_ATTN_FWD, 4.0 * p.B * p.A * p.S * p.S * kHd, 1);
+        attn_fwd_tc_kernel<<<grid, kThreadsTc, L.total, st>>>(tq, tkv, tp);
+    }
+    VB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace vb
