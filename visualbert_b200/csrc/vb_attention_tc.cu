@@ -208,28 +208,51 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             mbar_wait(bar(SFULL0 + sb), (li / tp.nsbuf) & 1);
             tcgen05_fence_after();
             const uint32_t ts = tmem_s(sb) + lane_sel;
-            // pass 1: row maximum of the scaled, masked scores
-            float m = -INFINITY;
-            for (int c = 0; c < nchunk; ++c) {
-                uint32_t v[16];
-                tmem_ld_32x32b_x16(ts + c * 16, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) m = fmaxf(m, fmaf(__uint_as_float(v[i]), sc2, sbias[c * 16 + i]));
-            }
-            // pass 2: probabilities, row sum, dropout, bf16 P tile in shared memory
             const int q = qt * kQRows + r;       // query index inside the head
-            float lsum = 0.f;
+            // Both passes stream the row out of TMEM in 16-column chunks with the NEXT chunk's tcgen05.ld already in
+            // flight (two statically named register buffers), and keep 4 independent max / sum chains.
+            // ---- pass 1: row maximum of the scaled, masked scores ----
+            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            auto pass1 = [&](const uint32_t (&v)[16], int c) {
+                const float4* b4 = reinterpret_cast<const float4*>(sbias + c * 16);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 bb = b4[j];
+                    mx[0] = fmaxf(mx[0], fmaf(__uint_as_float(v[4 * j]), sc2, bb.x));
+                    mx[1] = fmaxf(mx[1], fmaf(__uint_as_float(v[4 * j + 1]), sc2, bb.y));
+                    mx[2] = fmaxf(mx[2], fmaf(__uint_as_float(v[4 * j + 2]), sc2, bb.z));
+                    mx[3] = fmaxf(mx[3], fmaf(__uint_as_float(v[4 * j + 3]), sc2, bb.w));
+                }
+            };
+            {
+                uint32_t va[16], vb_[16];
+                tmem_ld_32x32b_x16(ts, va);
+                for (int c = 0; c < nchunk; c += 2) {
+                    tmem_ld_wait();
+                    if (c + 1 < nchunk) tmem_ld_32x32b_x16(ts + (c + 1) * 16, vb_);
+                    pass1(va, c);
+                    if (c + 1 < nchunk) {
+                        tmem_ld_wait();
+                        if (c + 2 < nchunk) tmem_ld_32x32b_x16(ts + (c + 2) * 16, va);
+                        pass1(vb_, c + 1);
+                    }
+                }
+            }
+            const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+            // ---- pass 2: probabilities, row sum, dropout, bf16 P tile in shared memory ----
+            float ls[4] = {0.f, 0.f, 0.f, 0.f};
             unsigned long long keepw = 0;        // keep bits of the current 64-key block
-            for (int c = 0; c < nchunk; ++c) {
-                uint32_t v[16];
-                tmem_ld_32x32b_x16(ts + c * 16, v);
-                tmem_ld_wait();
+            auto pass2 = [&](const uint32_t (&v)[16], int c) {
+                const float4* b4 = reinterpret_cast<const float4*>(sbias + c * 16);
                 float pr[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    pr[i] = fast_ex2(fmaf(__uint_as_float(v[i]), sc2, sbias[c * 16 + i]) - m);
-                    lsum += pr[i];
+                for (int j = 0; j < 4; ++j) {
+                    const float4 bb = b4[j];
+                    pr[4 * j] = fast_ex2(fmaf(__uint_as_float(v[4 * j]), sc2, bb.x) - m);
+                    pr[4 * j + 1] = fast_ex2(fmaf(__uint_as_float(v[4 * j + 1]), sc2, bb.y) - m);
+                    pr[4 * j + 2] = fast_ex2(fmaf(__uint_as_float(v[4 * j + 2]), sc2, bb.z) - m);
+                    pr[4 * j + 3] = fast_ex2(fmaf(__uint_as_float(v[4 * j + 3]), sc2, bb.w) - m);
+                    ls[0] += pr[4 * j]; ls[1] += pr[4 * j + 1]; ls[2] += pr[4 * j + 2]; ls[3] += pr[4 * j + 3];
                 }
                 if (p.drop_scale != 0.f) {
                     uint32_t bits = 0;
@@ -253,14 +276,28 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 // 16 keys = two 16-byte chunks of row r in the 64-key atom (c / 4)
                 const uint32_t atom = p_tile + (c >> 2) * (kQRows * 128) + r * 128;
                 const int ch0 = (c & 3) * 2;
-                uint4 w0, w1;
-                w0.x = pack_bf16x2(pr[0], pr[1]); w0.y = pack_bf16x2(pr[2], pr[3]);
-                w0.z = pack_bf16x2(pr[4], pr[5]); w0.w = pack_bf16x2(pr[6], pr[7]);
-                w1.x = pack_bf16x2(pr[8], pr[9]); w1.y = pack_bf16x2(pr[10], pr[11]);
-                w1.z = pack_bf16x2(pr[12], pr[13]); w1.w = pack_bf16x2(pr[14], pr[15]);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(atom + ((ch0 ^ (r & 7)) << 4)), "r"(w0.x), "r"(w0.y), "r"(w0.z), "r"(w0.w) : "memory");
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(atom + (((ch0 + 1) ^ (r & 7)) << 4)), "r"(w1.x), "r"(w1.y), "r"(w1.z), "r"(w1.w) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(atom + ((ch0 ^ (r & 7)) << 4)),
+                             "r"(pack_bf16x2(pr[0], pr[1])), "r"(pack_bf16x2(pr[2], pr[3])), "r"(pack_bf16x2(pr[4], pr[5])),
+                             "r"(pack_bf16x2(pr[6], pr[7])) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(atom + (((ch0 + 1) ^ (r & 7)) << 4)),
+                             "r"(pack_bf16x2(pr[8], pr[9])), "r"(pack_bf16x2(pr[10], pr[11])), "r"(pack_bf16x2(pr[12], pr[13])),
+                             "r"(pack_bf16x2(pr[14], pr[15])) : "memory");
+            };
+            {
+                uint32_t va[16], vb_[16];
+                tmem_ld_32x32b_x16(ts, va);
+                for (int c = 0; c < nchunk; c += 2) {
+                    tmem_ld_wait();
+                    if (c + 1 < nchunk) tmem_ld_32x32b_x16(ts + (c + 1) * 16, vb_);
+                    pass2(va, c);
+                    if (c + 1 < nchunk) {
+                        tmem_ld_wait();
+                        if (c + 2 < nchunk) tmem_ld_32x32b_x16(ts + (c + 2) * 16, va);
+                        pass2(vb_, c + 1);
+                    }
+                }
             }
+            const float lsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
             tcgen05_fence_before();
             mbar_arrive(bar(SEMPTY0 + sb));     // scores consumed: the next QK^T may overwrite this TMEM buffer
             fence_proxy_async_smem();            // P (generic-proxy stores) -> visible to the tensor core (async proxy)
