@@ -218,3 +218,19 @@ def test_attention_dropout_consistent_between_fwd_and_bwd():
     assert abs(lhs - rhs) < 2e-2 * max(abs(lhs), 1.0) + 2.0
     # mean over many rows: E[dropout(P)] = P, so the average output stays close to the no-dropout one
     assert abs(ctx.float().mean().item() - ref.mean().item()) < 5e-3
+
+
+@pytest.mark.parametrize("impl", ["tc", "staged"])
+def test_attention_alternative_implementations(impl):
+    """The tcgen05/TMEM forward kernel and the generic staged kernels must agree with the default whole-head kernels
+    (selected per process through VB_ATTN_FWD_IMPL / VB_ATTN_STAGED, so each runs in a subprocess)."""
+    import os, subprocess, sys
+    env = dict(os.environ)
+    env["VB_ATTN_FWD_IMPL"] = impl
+    if impl == "staged":
+        env["VB_ATTN_STAGED"] = "1"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_kernels_gpu.py"), "-m", "gpu", "-q",
+                        "-k", "attention_fwd_bwd or attention_dropout or attention_fully"], env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

