@@ -15,6 +15,7 @@
 // backward (input gradients use B "MN-major", weight gradients use A and B "MN-major").
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -380,6 +381,209 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a cluster of two CTAs on neighbouring SMs computes one 256 x 256 tile.
+// Each CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256 columns); the leader's single
+// tcgen05.mma.cta_group::2 (M = 256) reads both halves from both shared memories, so per-SM shared-memory
+// traffic per FLOP drops by a third and the ring fits 6 stages. Each CTA keeps its 128 x 256 fp32 accumulator
+// rows in its own TMEM and runs its own epilogue.
+//   full[s]   lives in the leader: 2 arrivals (leader: expect_tx of both CTAs' bytes; peer: remote arrive) + tx
+//   empty[s], tmem_full[a]  live in both CTAs, arrived by the leader's multicast tcgen05.commit
+//   tmem_empty[a]           lives in the leader: 2 x 256 epilogue-thread arrivals (peer arrives remotely)
+// ---------------------------------------------------------------------------------------------
+constexpr int kStages2 = 6;
+struct Cfg2 {
+    static constexpr int BLOCK_N = 256;
+    static constexpr int A_BYTES = 128 * BLOCK_K * 2;       // this CTA's 128 rows of A
+    static constexpr int B_BYTES = 128 * BLOCK_K * 2;       // this CTA's half of the 256 B rows
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFF = kStages2 * STAGE_BYTES;
+    static constexpr int NUM_BARS = 2 * kStages2 + 4;
+    static constexpr int TMEM_PTR_OFF = BAR_OFF + NUM_BARS * 8;
+    static constexpr int BIAS_OFF = TMEM_PTR_OFF + 16;
+    static constexpr int SMEM_BYTES = BIAS_OFF + 2 * BLOCK_N * 4 + 1024;
+    static constexpr int TMEM_COLS = 512;
+};
+
+__host__ __device__ constexpr uint32_t make_idesc_m(int m, int n, bool a_mn, bool b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn) << 15) |
+           (static_cast<uint32_t>(b_mn) << 16) | (static_cast<uint32_t>(n >> 3) << 17) |
+           (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+template <bool A_MN, bool B_MN, bool OUT_F32>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const GemmParams p) {
+    using C = Cfg2;
+    constexpr int BLOCK_N = 256;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    auto a_tile = [&](int s) { return base + s * C::STAGE_BYTES; };
+    auto b_tile = [&](int s) { return base + s * C::STAGE_BYTES + C::A_BYTES; };
+    auto full_bar = [&](int s) { return base + C::BAR_OFF + 8 * s; };
+    auto empty_bar = [&](int s) { return base + C::BAR_OFF + 8 * (kStages2 + s); };
+    auto tfull_bar = [&](int s) { return base + C::BAR_OFF + 8 * (2 * kStages2 + s); };
+    auto tempty_bar = [&](int s) { return base + C::BAR_OFF + 8 * (2 * kStages2 + 2 + s); };
+    volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + C::TMEM_PTR_OFF);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages2; ++s) {
+            mbar_init(full_bar(s), 2);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 2 * kEpiWarps * 32);
+        }
+        fence_barrier_init();
+    }
+    cluster_sync_all();  // barriers of both CTAs initialised before anyone signals across the pair
+    if (warp == 2) tmem_alloc_2cta(base + C::TMEM_PTR_OFF, C::TMEM_COLS);
+    tcgen05_fence_before();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int m_blocks = (p.M + 255) / 256;
+    const int n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
+    const int k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+    const int num_tiles = m_blocks * n_blocks * p.splits;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------- TMA producer (both CTAs) ----------------
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+                const TileCoord tc = decode_tile(t, n_blocks, p.splits, k_blocks);
+                const int m0 = tc.m_blk * 256 + static_cast<int>(rank) * 128;
+                const int n0 = tc.n_blk * BLOCK_N + static_cast<int>(rank) * 128;
+                for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
+                    else mbar_arrive_remote(full_bar(stage), 0);
+                    if constexpr (!A_MN) {
+                        tma_load_2d_2cta(a_tile(stage), &tmA, full_bar(stage), kb * BLOCK_K, m0);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+                            tma_load_2d_2cta(a_tile(stage) + i * kAtomBytes, &tmA, full_bar(stage), m0 + i * 64, kb * BLOCK_K);
+                    }
+                    if constexpr (!B_MN) {
+                        tma_load_2d_2cta(b_tile(stage), &tmB, full_bar(stage), kb * BLOCK_K, n0);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+                            tma_load_2d_2cta(b_tile(stage) + i * kAtomBytes, &tmB, full_bar(stage), n0 + i * 64, kb * BLOCK_K);
+                    }
+                    if (++stage == kStages2) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            // ---------------- MMA issuer (leader CTA only) ----------------
+            constexpr uint32_t idesc = make_idesc_m(256, BLOCK_N, A_MN, B_MN);
+            constexpr uint32_t a_kstep = A_MN ? UMMA_K * 128 : UMMA_K * 2;
+            constexpr uint32_t b_kstep = B_MN ? UMMA_K * 128 : UMMA_K * 2;
+            constexpr uint32_t a_lbo = A_MN ? kAtomBytes : 0;
+            constexpr uint32_t b_lbo = B_MN ? kAtomBytes : 0;
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+                const TileCoord tc = decode_tile(t, n_blocks, p.splits, k_blocks);
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tcgen05_fence_after();
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t ad = make_smem_desc(a_tile(stage) + k * a_kstep, a_lbo, 1024);
+                        const uint64_t bd = make_smem_desc(b_tile(stage) + k * b_kstep, b_lbo, 1024);
+                        umma_bf16_2cta(d_tmem, ad, bd, idesc, (kb > tc.kb_begin || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit_2cta(empty_bar(stage));
+                    if (kb == tc.kb_end - 1) umma_commit_2cta(tfull_bar(acc));
+                    if (++stage == kStages2) { stage = 0; phase ^= 1u; }
+                }
+            }
+            // the peer's epilogue arrives remotely on our tmem_empty barriers: wait for the last two tiles'
+            // arrivals before this CTA may exit (its shared memory must stay valid until then)
+            for (int j = (it >= 2 ? it - 2 : 0); j < it; ++j) mbar_wait(tempty_bar(j & 1), (j >> 1) & 1);
+        }
+    } else if (warp >= 4) {
+        // ---------------- epilogue (both CTAs, 128 rows each) ----------------
+        const int ew = warp - 4;
+        const int q = warp & 3;
+        const int half = ew >> 2;
+        const int et = threadIdx.x - 128;
+        float* sbias_all = reinterpret_cast<float*>(smem + C::BIAS_OFF);
+        constexpr int NCH = BLOCK_N / 2 / 16;
+        int it = 0;
+        for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+            const TileCoord tc = decode_tile(t, n_blocks, p.splits, k_blocks);
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const bool has_bias = p.bias != nullptr;
+            float* sb = sbias_all + acc * BLOCK_N;
+            if (has_bias) {
+                const bool mine = p.splits == 1 || (t % p.splits) == 0;
+                for (int i = et; i < BLOCK_N; i += kEpiWarps * 32) {
+                    const int col = tc.n_blk * BLOCK_N + i;
+                    sb[i] = (mine && col < p.N) ? __ldg(p.bias + col) : 0.f;
+                }
+                named_bar_sync(1, kEpiWarps * 32);
+            }
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tcgen05_fence_after();
+            const int row = tc.m_blk * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;
+            const int col0 = tc.n_blk * BLOCK_N + half * (BLOCK_N / 2);
+            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + half * (BLOCK_N / 2);
+            uint32_t v[2][16];
+            tmem_ld_32x32b_x16(taddr0, v[0]);
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+                tmem_ld_wait();
+                if (k + 1 < NCH) tmem_ld_32x32b_x16(taddr0 + (k + 1) * 16, v[(k + 1) & 1]);
+                const int col = col0 + k * 16;
+                if (row < p.M && col < p.N) {
+                    float x[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[k & 1][i]);
+                    epilogue16<OUT_F32>(p, row, col, has_bias ? sb + half * (BLOCK_N / 2) + k * 16 : nullptr, x);
+                }
+            }
+            tcgen05_fence_before();
+            if (leader) mbar_arrive(tempty_bar(acc));
+            else mbar_arrive_remote(tempty_bar(acc), 0);
+        }
+    }
+
+    tcgen05_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc_2cta(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -452,6 +656,32 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
     return 0;
 }
 
+template <bool A_MN, bool B_MN, bool OUT_F32>
+static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+    auto kern = gemm_tcgen05_2cta_kernel<A_MN, B_MN, OUT_F32>;
+    static bool configured = false;
+    if (!configured) {
+        VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES));
+        configured = true;
+    }
+    const int tiles = ((p.M + 255) / 256) * ((p.N + 255) / 256) * p.splits;
+    int clusters = num_sms() / 2;
+    if (clusters > tiles) clusters = tiles;
+    {
+        ProfScope ps(st, OUT_F32 ? PROF_GEMM_WGRAD : (B_MN ? PROF_GEMM_DGRAD : PROF_GEMM_FWD), 2.0 * p.M * p.N * p.K, 1);
+        kern<<<2 * clusters, kThreads, Cfg2::SMEM_BYTES, st>>>(ta, tb, p);
+    }
+    VB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// VB_GEMM_2CTA=0 disables the CTA-pair kernels (testing / tuning)
+static bool use_2cta() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VB_GEMM_2CTA"); v = (e != nullptr && atoi(e) == 0) ? 0 : 1; }
+    return v == 1;
+}
+
 int gemm(const vb_gemm_args& a, cudaStream_t st) {
     VB_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "vb_gemm: empty problem M=%d N=%d K=%d", a.M, a.N, a.K);
     VB_REQUIRE(a.N % 16 == 0, "vb_gemm: N=%d must be a multiple of 16", a.N);
@@ -494,6 +724,26 @@ int gemm(const vb_gemm_args& a, cudaStream_t st) {
 
     CUtensorMap ta, tb;
     int rc;
+    // CTA-pair kernel: 256 x 256 tiles, each CTA loads 128-row boxes of A and of its half of B
+    if (use_2cta() && bn256 && a.M >= 256) {
+        if (!a.a_mn_major) rc = make_tmap_bf16(&ta, a.A, a.K, a.M, a.lda, 128);
+        else               rc = make_tmap_bf16(&ta, a.A, a.M, a.K, a.lda, BLOCK_K);
+        if (rc) return rc;
+        if (!a.b_mn_major) rc = make_tmap_bf16(&tb, a.B, a.K, a.N, a.ldb, 128);
+        else               rc = make_tmap_bf16(&tb, a.B, a.N, a.K, a.ldb, BLOCK_K);
+        if (rc) return rc;
+        if (!a.d_fp32) {
+            if (!a.a_mn_major && !a.b_mn_major) return launch2<false, false, false>(ta, tb, p, st);
+            if (!a.a_mn_major && a.b_mn_major) return launch2<false, true, false>(ta, tb, p, st);
+            if (a.a_mn_major && a.b_mn_major) return launch2<true, true, false>(ta, tb, p, st);
+            return launch2<true, false, false>(ta, tb, p, st);
+        } else {
+            if (!a.a_mn_major && !a.b_mn_major) return launch2<false, false, true>(ta, tb, p, st);
+            if (!a.a_mn_major && a.b_mn_major) return launch2<false, true, true>(ta, tb, p, st);
+            if (a.a_mn_major && a.b_mn_major) return launch2<true, true, true>(ta, tb, p, st);
+            return launch2<true, false, true>(ta, tb, p, st);
+        }
+    }
     if (!a.a_mn_major) rc = make_tmap_bf16(&ta, a.A, a.K, a.M, a.lda, BLOCK_M);
     else               rc = make_tmap_bf16(&ta, a.A, a.M, a.K, a.lda, BLOCK_K);
     if (rc) return rc;
