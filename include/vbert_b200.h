@@ -107,6 +107,16 @@ int vb_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream); /
 int vb_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream);
 int vb_colsum_bf16(const void* x, int64_t ld, float* out, int32_t rows, int32_t cols, void* stream); /* out += */
 
+/* ---- masked-LM loss (M.py:1471-1473, CrossEntropyLoss(ignore_index=-1) on the labelled rows) ------------- */
+/* logits bf16 [rows, ld] with valid columns [0, vocab); labels int64 [rows] in [0, vocab).
+ * fwd: lse[row] = logsumexp(logits[row, :vocab]), loss_rows[row] = lse - logits[row, label].
+ * bwd: logits[row, c] <- (softmax - onehot) * (*scale) for c < vocab and 0 for vocab <= c < padded_cols, IN PLACE
+ *      (scale is a device scalar: upstream gradient / number of labelled rows). */
+int vb_cross_entropy_fwd(const void* logits, int64_t ld, const int64_t* labels, int32_t rows, int32_t vocab, float* lse,
+                         float* loss_rows, void* stream);
+int vb_cross_entropy_bwd(void* logits, int64_t ld, const int64_t* labels, int32_t rows, int32_t vocab, int32_t padded_cols,
+                         const float* lse, const float* scale, void* stream);
+
 /* ---- BertLayer (M.py:322-341) ------------------------------------------------------------ */
 typedef struct {
     int32_t batch, seq, hidden, heads, inter;

@@ -234,3 +234,29 @@ def test_attention_alternative_implementations(impl):
                         "-k", "attention_fwd_bwd or attention_dropout or attention_fully"], env=env, capture_output=True, text=True,
                        timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("n,V", [(300, 30522), (77, 1000), (5, 512)])
+def test_mlm_decoder_and_fused_cross_entropy(n, V):
+    """ops.mlm_decoder + ops.cross_entropy_rows against F.linear + F.cross_entropy (fp32) incl. gradients."""
+    from visualbert_b200 import ops
+    dev = torch.device("cuda:0")
+    torch.manual_seed(11)
+    H = 768
+    E = (0.05 * torch.randn(V, H, device=dev)).requires_grad_(True)
+    bias = (0.1 * torch.randn(V, device=dev)).requires_grad_(True)
+    t0 = torch.randn(n, H, device=dev).bfloat16()
+    labels = torch.randint(0, V, (n,), device=dev)
+    t = t0.clone().requires_grad_(True)
+    cache = ops.DecoderWeights()
+    logits = ops.mlm_decoder(t, E, bias, cache)
+    assert logits.shape == (n, (V + 15) // 16 * 16)
+    loss = ops.cross_entropy_rows(logits, labels, V)
+    (loss * 3.0).backward()
+    tr = t0.float().requires_grad_(True); Er = E.detach().bfloat16().float().requires_grad_(True); br = bias.detach().clone().requires_grad_(True)
+    lr = torch.nn.functional.cross_entropy(tr @ Er.t() + br, labels)
+    (lr * 3.0).backward()
+    assert abs(loss.item() - lr.item()) < 2e-3 * abs(lr.item())
+    assert _rel(t.grad, tr.grad) < 2e-2
+    assert _rel(E.grad, Er.grad) < 2e-2
+    assert _rel(bias.grad, br.grad) < 2e-2

@@ -556,8 +556,16 @@ class TrainVisualBERTObjective(PreTrainedBertModel):
         labels = flat_labels.contiguous().view(-1)
         rows = torch.nonzero(labels != -1).squeeze(1)
         hidden = sequence_output.reshape(-1, sequence_output.size(-1)).index_select(0, rows)
-        scores = self.cls.predictions(hidden)
-        return F.cross_entropy(scores.float(), labels.index_select(0, rows))
+        head = self.cls.predictions
+        if rows.numel() == 0 or not hidden.is_cuda:
+            return F.cross_entropy(head(hidden).float(), labels.index_select(0, rows))
+        # decoder + loss on the library's kernels: tcgen05 GEMMs (fwd / dgrad / wgrad into the tied word-embedding
+        # gradient) and the fused cross-entropy; the small transform (dense + gelu + LayerNorm on ~12 % of the rows)
+        # stays PyTorch
+        if not hasattr(self, "_decoder_weights"):
+            self._decoder_weights = ops.DecoderWeights()
+        scores = ops.mlm_decoder(head.transform(hidden), head.decoder.weight, head.bias, self._decoder_weights)
+        return ops.cross_entropy_rows(scores, labels.index_select(0, rows), head.decoder.weight.size(0))
 
     def forward(self, input_ids, token_type_ids, input_mask, visual_embeddings, position_embeddings_visual, image_mask,
                 image_text_alignment=None, confidence=None, visual_embeddings_type=None, label=None,

@@ -331,3 +331,118 @@ class _EmbedFn(torch.autograd.Function):
 def bert_embeddings(meta, input_ids, token_type_ids, visual_type, feats, word, pos, typ, typ_vis, pos_vis, pw, pb, gamma, beta):
     return _EmbedFn.apply(meta, input_ids, token_type_ids, visual_type, feats, word, pos, typ, typ_vis, pos_vis, pw, pb,
                           gamma, beta)
+
+
+# --------------------------------------------------------------------------------------------
+# masked-LM head on the library's kernels: decoder GEMMs on tcgen05, fused cross-entropy
+# --------------------------------------------------------------------------------------------
+def _gemm(**kw):
+    a = _lib.GemmArgs()
+    for k, v in kw.items():
+        setattr(a, k, v)
+    _lib.check(_lib.lib().vb_gemm(ctypes.byref(a), _stream()), "vb_gemm")
+
+
+class DecoderWeights:
+    """bf16 copy of the tied word-embedding matrix [vocab, H] and the fp32 bias padded to a multiple of 16 columns
+    (padding columns get -30000 so they vanish in the softmax), refreshed when the masters change."""
+
+    def __init__(self):
+        self.key = None
+        self.table = None
+        self.bias = None
+
+    def get(self, E, bias):
+        key = (E.data_ptr(), E._version, bias.data_ptr(), bias._version)
+        if key != self.key:
+            V = E.shape[0]
+            Vp = (V + 15) // 16 * 16
+            with torch.no_grad():
+                self.table = cast_to_bf16(E.detach(), self.table if self.table is not None and self.table.device == E.device else None)
+                if self.bias is None or self.bias.device != E.device or self.bias.numel() != Vp:
+                    self.bias = torch.full((Vp,), -30000.0, device=E.device, dtype=torch.float32)
+                self.bias[:V].copy_(bias.detach())
+            self.key = key
+        return self.table, self.bias
+
+
+class _MlmDecoderFn(torch.autograd.Function):
+    """logits[n, Vp] = t[n, H] @ E[V, H]^T + bias (BertLMPredictionHead decoder, reference M.py:403-421) — forward,
+    input-gradient and weight-gradient GEMMs all on gemm_tcgen05_kernel; the weight gradient accumulates straight
+    into the (tied) word-embedding gradient when that buffer exists."""
+
+    @staticmethod
+    def forward(ctx, t, E, bias, cache):
+        _require_cuda(t, "mlm_decoder")
+        n, H = t.shape
+        V = E.shape[0]
+        Vp = (V + 15) // 16 * 16
+        table, bias_p = cache.get(E, bias)
+        t = t.to(_BF16).contiguous()
+        logits = torch.empty(n, Vp, device=t.device, dtype=_BF16)
+        _gemm(A=t.data_ptr(), lda=H, B=table.data_ptr(), ldb=H, M=n, N=Vp, K=H, D=logits.data_ptr(), ldd=Vp,
+              bias=bias_p.data_ptr())
+        ctx.save_for_backward(t, table)
+        ctx.E, ctx.bias, ctx.V = E, bias, V
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        t, table = ctx.saved_tensors
+        E, bias, V = ctx.E, ctx.bias, ctx.V
+        n, H = t.shape
+        Vp = dlogits.shape[1]
+        dlogits = dlogits.contiguous()
+        dt = torch.empty(n, H, device=t.device, dtype=_BF16)
+        _gemm(A=dlogits.data_ptr(), lda=Vp, B=table.data_ptr(), ldb=H, b_mn_major=1, M=n, N=H, K=Vp, D=dt.data_ptr(), ldd=H)
+        direct = _grad_targets((E, bias))
+        if direct is not None:
+            dE, db = direct
+            db_pad = torch.zeros(Vp, device=t.device, dtype=torch.float32)
+        else:
+            dE = torch.zeros(V, H, device=t.device, dtype=torch.float32)
+            db_pad = torch.zeros(Vp, device=t.device, dtype=torch.float32)
+        _gemm(A=dlogits.data_ptr(), lda=Vp, a_mn_major=1, B=t.data_ptr(), ldb=H, b_mn_major=1, M=V, N=H, K=n,
+              D=dE.data_ptr(), ldd=H, d_fp32=1, splits=1)
+        _lib.check(_lib.lib().vb_colsum_bf16(ctypes.c_void_p(dlogits.data_ptr()), ctypes.c_int64(Vp), ctypes.c_void_p(db_pad.data_ptr()),
+                                             n, Vp, _stream()), "vb_colsum_bf16")
+        if direct is not None:
+            db.add_(db_pad[:V])
+            return dt, None, None, None
+        return dt, dE, db_pad[:V].clone(), None
+
+
+def mlm_decoder(t, E, bias, cache):
+    return _MlmDecoderFn.apply(t, E, bias, cache)
+
+
+class _CrossEntropyFn(torch.autograd.Function):
+    """mean over rows of (logsumexp(logits[:, :V]) - logits[row, label]); the backward overwrites the logits with
+    their gradient in place (vb_cross_entropy_bwd)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, V):
+        n, Vp = logits.shape
+        labels = labels.to(torch.int64).contiguous()
+        lse = torch.empty(n, device=logits.device, dtype=torch.float32)
+        rows = torch.empty(n, device=logits.device, dtype=torch.float32)
+        _lib.check(_lib.lib().vb_cross_entropy_fwd(ctypes.c_void_p(logits.data_ptr()), ctypes.c_int64(Vp),
+                                                   ctypes.c_void_p(labels.data_ptr()), n, V, ctypes.c_void_p(lse.data_ptr()),
+                                                   ctypes.c_void_p(rows.data_ptr()), _stream()), "vb_cross_entropy_fwd")
+        ctx.logits, ctx.labels, ctx.lse, ctx.V = logits, labels, lse, V
+        return rows.mean()
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, labels, lse, V = ctx.logits, ctx.labels, ctx.lse, ctx.V
+        n, Vp = logits.shape
+        scale = (g.float() / n).reshape(1).contiguous()
+        _lib.check(_lib.lib().vb_cross_entropy_bwd(ctypes.c_void_p(logits.data_ptr()), ctypes.c_int64(Vp),
+                                                   ctypes.c_void_p(labels.data_ptr()), n, V, Vp, ctypes.c_void_p(lse.data_ptr()),
+                                                   ctypes.c_void_p(scale.data_ptr()), _stream()), "vb_cross_entropy_bwd")
+        ctx.logits = None
+        return logits, None, None
+
+
+def cross_entropy_rows(logits, labels, V):
+    return _CrossEntropyFn.apply(logits, labels, V)
