@@ -358,7 +358,10 @@ class DecoderWeights:
             V = E.shape[0]
             Vp = (V + 15) // 16 * 16
             with torch.no_grad():
-                self.table = cast_to_bf16(E.detach(), self.table if self.table is not None and self.table.device == E.device else None)
+                # [Vp, H] with zero rows V..Vp-1: the GEMMs address all Vp rows of the table
+                if self.table is None or self.table.device != E.device or self.table.shape[0] != Vp:
+                    self.table = torch.zeros(Vp, E.shape[1], device=E.device, dtype=_BF16)
+                cast_to_bf16(E.detach(), self.table[:V])
                 if self.bias is None or self.bias.device != E.device or self.bias.numel() != Vp:
                     self.bias = torch.full((Vp,), -30000.0, device=E.device, dtype=torch.float32)
                 self.bias[:V].copy_(bias.detach())
