@@ -8,10 +8,12 @@
 //                             O = P V     tcgen05.mma 128 x 64 x 16, Npad/16 k-steps, P read from shared memory
 //                                          (K-major, 128B-swizzled A tile written by the softmax warps), V MN-major
 //   warp 2      TMEM allocator
-//   warps 4-7   softmax + epilogue: one thread per query row (TMEM lane): row max and exp2 straight from TMEM
-//               (two passes, no online rescaling needed because the whole key range is in TMEM), attention dropout
-//               (keep-mask drawn here and stored packed for the backward), P -> bf16 -> swizzled smem tile,
-//               then O * 1/l -> bf16 -> one contiguous 128-byte row store per thread, LSE for the backward.
+//   warps 4-19  softmax + epilogue, 4 warp-groups: row r of the tile is TMEM lane r, and its key range is split
+//               over 4 threads (warp-group g owns the 16-column chunks c = g, g+4, ...), so every SM sub-partition
+//               has 4 softmax warps to hide ALU/SFU/TMEM latency. Row max and exp2 straight from TMEM (two passes,
+//               no online rescaling because the whole key range is in TMEM; partial max / sum exchanged through
+//               shared memory), attention dropout (keep-mask drawn here and stored packed for the backward),
+//               P -> bf16 -> swizzled smem tile, then O * 1/l -> bf16 -> 32-byte stores, LSE for the backward.
 //
 // Same math as reference modeling.py:241-256 (scale, additive mask, softmax, dropout, P V, head merge).
 #include "vb_attention.cuh"
@@ -21,8 +23,9 @@ namespace vb {
 namespace {
 
 constexpr int kQRows = 128;            // query rows per work item (UMMA M)
-constexpr int kThreadsTc = 256;
-constexpr int kSoftmaxThreads = 128;
+constexpr int kSoftmaxWgs = 4;          // softmax warp-groups: each row's key range is split over 4 threads
+constexpr int kSoftmaxThreads = 128 * kSoftmaxWgs;
+constexpr int kThreadsTc = 128 + kSoftmaxThreads;
 
 __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
     asm volatile(
@@ -53,6 +56,7 @@ struct TcLayout {  // shared-memory carve-up (bytes), all tile bases 1 KB aligne
     int nstage;
     int p_off, p_bytes;
     int bias_off;      // fp32 [2][256]
+    int xchg_off;
     int bar_off;
     int tmem_ptr_off;
     int total;
@@ -65,7 +69,8 @@ __host__ __device__ inline TcLayout tc_layout(int npad, int nstage) {
     L.p_off = nstage * L.stage_bytes;
     L.p_bytes = ((npad + 63) / 64) * kQRows * 128;
     L.bias_off = L.p_off + L.p_bytes;
-    L.bar_off = L.bias_off + 2 * 256 * 4;
+    L.xchg_off = L.bias_off + 2 * 256 * 4;                       // fp32 [2 parities][max|sum][4 wgs][128 rows]
+    L.bar_off = L.xchg_off + 2 * 2 * kSoftmaxWgs * 128 * 4;
     L.tmem_ptr_off = L.bar_off + 16 * 8;
     L.total = L.tmem_ptr_off + 16 + 1024;
     return L;
@@ -188,30 +193,40 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             }
         }
     } else if (warp >= 4) {
-        // ---------------- softmax + epilogue: one thread per query row ----------------
-        const int q4 = warp & 3;
+        // ---------------- softmax + epilogue: 4 threads per query row ----------------
+        const int q4 = warp & 3;                 // TMEM lane quarter of this warp
+        const int wg = (warp - 4) >> 2;          // warp-group 0..3 = column phase
         const int r = q4 * 32 + lane;            // row inside the 128-row tile == TMEM lane
-        const int st = threadIdx.x - 128;        // 0..127
+        const int st = threadIdx.x - 128;        // 0..511
         const uint32_t lane_sel = static_cast<uint32_t>(q4 * 32) << 16;
         float* sbias_all = reinterpret_cast<float*>(smem + L.bias_off);
+        float* xchg_all = reinterpret_cast<float*>(smem + L.xchg_off);
         const float sc2 = p.scale * kLog2e;
         const int nchunk = npad / 16;
+        auto stage_bias = [&](int li) {
+            int b, h, qt;
+            decode(li, b, h, qt);
+            float* sb = sbias_all + (li & 1) * 256;
+            for (int i = st; i < npad; i += kSoftmaxThreads)
+                sb[i] = i < S ? p.mask_bias[static_cast<long long>(b) * S + i] * kLog2e : -INFINITY;
+        };
+        if (n_local > 0) stage_bias(0);
+        named_bar_sync(2, kSoftmaxThreads);
         for (int li = 0; li < n_local; ++li) {
             int b, h, qt;
             decode(li, b, h, qt);
             const int sb = li % tp.nsbuf;
             const unsigned bh = static_cast<unsigned>(b * p.A + h);
-            float* sbias = sbias_all + (li & 1) * 256;
-            for (int i = st; i < npad; i += kSoftmaxThreads)
-                sbias[i] = i < S ? p.mask_bias[static_cast<long long>(b) * S + i] * kLog2e : -INFINITY;
-            named_bar_sync(2, kSoftmaxThreads);
+            const float* sbias = sbias_all + (li & 1) * 256;
+            float* xmax = xchg_all + (li & 1) * (2 * kSoftmaxWgs * 128);
+            float* xsum = xmax + kSoftmaxWgs * 128;
+            if (li + 1 < n_local) stage_bias(li + 1);   // visible to everyone after this item's named barrier
             mbar_wait(bar(SFULL0 + sb), (li / tp.nsbuf) & 1);
             tcgen05_fence_after();
             const uint32_t ts = tmem_s(sb) + lane_sel;
             const int q = qt * kQRows + r;       // query index inside the head
-            // Both passes stream the row out of TMEM in 16-column chunks with the NEXT chunk's tcgen05.ld already in
-            // flight (two statically named register buffers), and keep 4 independent max / sum chains.
-            // ---- pass 1: row maximum of the scaled, masked scores ----
+            // Each thread streams ITS chunks (c = wg, wg+4, ...) out of TMEM with the next chunk's tcgen05.ld in flight.
+            // ---- pass 1: partial row maximum of the scaled, masked scores ----
             float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
             auto pass1 = [&](const uint32_t (&v)[16], int c) {
                 const float4* b4 = reinterpret_cast<const float4*>(sbias + c * 16);
@@ -226,22 +241,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             };
             {
                 uint32_t va[16], vb_[16];
-                tmem_ld_32x32b_x16(ts, va);
-                for (int c = 0; c < nchunk; c += 2) {
+                if (wg < nchunk) tmem_ld_32x32b_x16(ts + wg * 16, va);
+                for (int c = wg; c < nchunk; c += 2 * kSoftmaxWgs) {
                     tmem_ld_wait();
-                    if (c + 1 < nchunk) tmem_ld_32x32b_x16(ts + (c + 1) * 16, vb_);
+                    if (c + kSoftmaxWgs < nchunk) tmem_ld_32x32b_x16(ts + (c + kSoftmaxWgs) * 16, vb_);
                     pass1(va, c);
-                    if (c + 1 < nchunk) {
+                    if (c + kSoftmaxWgs < nchunk) {
                         tmem_ld_wait();
-                        if (c + 2 < nchunk) tmem_ld_32x32b_x16(ts + (c + 2) * 16, va);
-                        pass1(vb_, c + 1);
+                        if (c + 2 * kSoftmaxWgs < nchunk) tmem_ld_32x32b_x16(ts + (c + 2 * kSoftmaxWgs) * 16, va);
+                        pass1(vb_, c + kSoftmaxWgs);
                     }
                 }
             }
-            const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-            // ---- pass 2: probabilities, row sum, dropout, bf16 P tile in shared memory ----
+            xmax[wg * 128 + r] = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+            named_bar_sync(2, kSoftmaxThreads);
+            const float m = fmaxf(fmaxf(xmax[r], xmax[128 + r]), fmaxf(xmax[256 + r], xmax[384 + r]));
+            // ---- pass 2: probabilities, partial row sum, dropout, bf16 P tile in shared memory ----
             float ls[4] = {0.f, 0.f, 0.f, 0.f};
-            unsigned long long keepw = 0;        // keep bits of the current 64-key block
             auto pass2 = [&](const uint32_t (&v)[16], int c) {
                 const float4* b4 = reinterpret_cast<const float4*>(sbias + c * 16);
                 float pr[16];
@@ -266,12 +282,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     }
 #pragma unroll
                     for (int i = 0; i < 16; ++i) pr[i] = ((bits >> i) & 1u) ? pr[i] * p.drop_scale : 0.f;
-                    keepw |= static_cast<unsigned long long>(bits) << ((c & 3) * 16);
-                    if ((c & 3) == 3 || c == nchunk - 1) {
-                        if (q < tp.nkb * kBlk)
-                            p.keep[(static_cast<unsigned long long>(bh) * (tp.nkb * kBlk) + q) * tp.nkb + (c >> 2)] = keepw;
-                        keepw = 0;
-                    }
+                    // chunk c = 16 keys = the 16-bit slice (c & 3) of the 64-bit keep word (c >> 2) of this query row
+                    if (q < tp.nkb * kBlk)
+                        reinterpret_cast<unsigned short*>(p.keep)[((static_cast<unsigned long long>(bh) * (tp.nkb * kBlk) + q) * tp.nkb + (c >> 2)) * 4 + (c & 3)] =
+                            static_cast<unsigned short>(bits);
                 }
                 // 16 keys = two 16-byte chunks of row r in the 64-key atom (c / 4)
                 const uint32_t atom = p_tile + (c >> 2) * (kQRows * 128) + r * 128;
@@ -285,44 +299,41 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             };
             {
                 uint32_t va[16], vb_[16];
-                tmem_ld_32x32b_x16(ts, va);
-                for (int c = 0; c < nchunk; c += 2) {
+                if (wg < nchunk) tmem_ld_32x32b_x16(ts + wg * 16, va);
+                for (int c = wg; c < nchunk; c += 2 * kSoftmaxWgs) {
                     tmem_ld_wait();
-                    if (c + 1 < nchunk) tmem_ld_32x32b_x16(ts + (c + 1) * 16, vb_);
+                    if (c + kSoftmaxWgs < nchunk) tmem_ld_32x32b_x16(ts + (c + kSoftmaxWgs) * 16, vb_);
                     pass2(va, c);
-                    if (c + 1 < nchunk) {
+                    if (c + kSoftmaxWgs < nchunk) {
                         tmem_ld_wait();
-                        if (c + 2 < nchunk) tmem_ld_32x32b_x16(ts + (c + 2) * 16, va);
-                        pass2(vb_, c + 1);
+                        if (c + 2 * kSoftmaxWgs < nchunk) tmem_ld_32x32b_x16(ts + (c + 2 * kSoftmaxWgs) * 16, va);
+                        pass2(vb_, c + kSoftmaxWgs);
                     }
                 }
             }
-            const float lsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
+            xsum[wg * 128 + r] = (ls[0] + ls[1]) + (ls[2] + ls[3]);  // read after OFULL (ordered by the mbarrier chain)
             tcgen05_fence_before();
             mbar_arrive(bar(SEMPTY0 + sb));     // scores consumed: the next QK^T may overwrite this TMEM buffer
             fence_proxy_async_smem();            // P (generic-proxy stores) -> visible to the tensor core (async proxy)
             mbar_arrive(bar(PFULL));
-            // epilogue: O row * 1/l -> bf16 -> 128 contiguous bytes
+            // epilogue: warp-group g owns O columns 16g .. 16g+15 of its row
             mbar_wait(bar(OFULL), li & 1);
             tcgen05_fence_after();
-            uint32_t o[4][16];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x16(tmem_o + lane_sel + c * 16, o[c]);
+            uint32_t o[16];
+            tmem_ld_32x32b_x16(tmem_o + lane_sel + wg * 16, o);
             tmem_ld_wait();
             tcgen05_fence_before();
             mbar_arrive(bar(OEMPTY));
             if (q < S) {
+                const float lsum = (xsum[r] + xsum[128 + r]) + (xsum[256 + r] + xsum[384 + r]);
                 const float inv = 1.f / lsum;
-                bf16* dst = p.ctx + (static_cast<long long>(b) * S + q) * p.H + h * kHd;
+                bf16* dst = p.ctx + (static_cast<long long>(b) * S + q) * p.H + h * kHd + wg * 16;
+                uint32_t w[8];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {  // 16 columns -> 16 bf16 = one 32-byte store
-                    uint32_t w[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        w[i] = pack_bf16x2(__uint_as_float(o[c][2 * i]) * inv, __uint_as_float(o[c][2 * i + 1]) * inv);
-                    stg_v8(dst + c * 16, w);
-                }
-                if (p.lse != nullptr)
+                for (int i = 0; i < 8; ++i)
+                    w[i] = pack_bf16x2(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
+                stg_v8(dst, w);
+                if (wg == 0 && p.lse != nullptr)
                     p.lse[(static_cast<long long>(b) * p.A + h) * S + q] = (m + log2f(lsum)) * 0.6931471805599453f;
             }
         }
