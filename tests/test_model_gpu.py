@@ -188,3 +188,28 @@ def test_direct_gradient_accumulation_matches_autograd_path():
                 a, b = p.grad.float(), want[k].float()
                 assert (a - b).norm().item() <= 2e-3 * b.norm().item() + 1e-7, k
     assert sync.flat.data_ptr() <= model.bert.encoder.layer[1].output.dense.weight.grad.data_ptr()
+
+
+def test_large_config_shapes_match_oracle():
+    """BASELINE configs[4] geometry (VisualBERT-large: H=1024, 16 heads, I=4096, 100 regions + 256 tokens => S=356, which
+    takes the staged attention kernels) at a reduced depth/batch: forward + backward against the fp32 oracle on the GPU."""
+    from visualbert_b200 import BertConfig, TrainVisualBERTObjective, synthetic
+    dev = torch.device("cuda:0")
+    cfg = synthetic.bert_config_dict(2, 1024, 16, 4096, vocab=2048)
+    sd = synthetic.init_state_dict(cfg, "pretraining", 2048, seed=3)
+    batch = synthetic.make_batch(3, 256, 100, 2048, head="pretraining", seed=7, vocab=2048, ragged=True)
+    batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    model = TrainVisualBERTObjective(BertConfig.from_dict(cfg), "pretraining", visual_embedding_dim=2048)
+    model.load_state_dict(sd, strict=False)
+    model.to(dev).eval()
+    out = model(**batch)
+    out["loss"].backward()
+    sdo = {k: v.to(dev).requires_grad_(True) for k, v in sd.items()}
+    ref = vb_oracle.objective(sdo, cfg, "pretraining", **{k: v for k, v in batch.items() if k != "position_embeddings_visual"})
+    ref["loss"].backward()
+    assert abs(out["loss"].item() - ref["loss"].item()) <= LOSS_RTOL * abs(ref["loss"].item())
+    for k in ("bert.encoder.layer.0.attention.self.key.weight", "bert.encoder.layer.1.intermediate.dense.weight",
+              "bert.embeddings.projection.weight", "bert.encoder.layer.0.output.LayerNorm.weight"):
+        a, b = dict(model.named_parameters())[k].grad.float().reshape(-1), sdo[k].grad.reshape(-1)
+        cos = torch.dot(a, b).item() / (a.norm().item() * b.norm().item())
+        assert cos >= GRAD_COS, f"{k}: cosine {cos:.5f}"

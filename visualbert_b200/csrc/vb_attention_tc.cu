@@ -83,6 +83,7 @@ struct TcParams {
     int nkb;       // ceil(S / 64)
     int nstage;    // input stages (2 if they fit)
     int nsbuf;     // TMEM score buffers (2 if they fit)
+    long long* dbg; // optional: clock64 stamps of CTA 0 (VB_TC_DEBUG=1), [16 items][8 stamps]
 };
 
 __global__ void __launch_bounds__(kThreadsTc, 1)
@@ -220,9 +221,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const float* sbias = sbias_all + (li & 1) * 256;
             float* xmax = xchg_all + (li & 1) * (2 * kSoftmaxWgs * 128);
             float* xsum = xmax + kSoftmaxWgs * 128;
+            const bool stamp = tp.dbg != nullptr && blockIdx.x == 0 && st == 0 && li < 16;
+            if (stamp) tp.dbg[li * 8 + 0] = clock64();
             if (li + 1 < n_local) stage_bias(li + 1);   // visible to everyone after this item's named barrier
             mbar_wait(bar(SFULL0 + sb), (li / tp.nsbuf) & 1);
             tcgen05_fence_after();
+            if (stamp) tp.dbg[li * 8 + 1] = clock64();
             const uint32_t ts = tmem_s(sb) + lane_sel;
             const int q = qt * kQRows + r;       // query index inside the head
             // Each thread streams ITS chunks (c = wg, wg+4, ...) out of TMEM with the next chunk's tcgen05.ld in flight.
@@ -254,7 +258,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 }
             }
             xmax[wg * 128 + r] = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+            if (stamp) tp.dbg[li * 8 + 2] = clock64();
             named_bar_sync(2, kSoftmaxThreads);
+            if (stamp) tp.dbg[li * 8 + 3] = clock64();
             const float m = fmaxf(fmaxf(xmax[r], xmax[128 + r]), fmaxf(xmax[256 + r], xmax[384 + r]));
             // ---- pass 2: probabilities, partial row sum, dropout, bf16 P tile in shared memory ----
             float ls[4] = {0.f, 0.f, 0.f, 0.f};
@@ -312,6 +318,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 }
             }
             xsum[wg * 128 + r] = (ls[0] + ls[1]) + (ls[2] + ls[3]);  // read after OFULL (ordered by the mbarrier chain)
+            if (stamp) tp.dbg[li * 8 + 4] = clock64();
             tcgen05_fence_before();
             mbar_arrive(bar(SEMPTY0 + sb));     // scores consumed: the next QK^T may overwrite this TMEM buffer
             fence_proxy_async_smem();            // P (generic-proxy stores) -> visible to the tensor core (async proxy)
@@ -319,6 +326,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             // epilogue: warp-group g owns O columns 16g .. 16g+15 of its row
             mbar_wait(bar(OFULL), li & 1);
             tcgen05_fence_after();
+            if (stamp) tp.dbg[li * 8 + 5] = clock64();
             uint32_t o[16];
             tmem_ld_32x32b_x16(tmem_o + lane_sel + wg * 16, o);
             tmem_ld_wait();
@@ -336,6 +344,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 if (wg == 0 && p.lse != nullptr)
                     p.lse[(static_cast<long long>(b) * p.A + h) * S + q] = (m + log2f(lsum)) * 0.6931471805599453f;
             }
+            if (stamp) tp.dbg[li * 8 + 6] = clock64();
         }
     }
     tcgen05_fence_before();
@@ -397,11 +406,28 @@ int attn_fwd_tc(const AttnParams& p, cudaStream_t st) {
     }
     const int total = p.B * p.A * tp.nq;
     const int grid = total < num_sms() ? total : num_sms();
+    static long long* dbg_buf = nullptr;
+    static int dbg_calls = 0;
+    const char* de = getenv("VB_TC_DEBUG");
+    tp.dbg = nullptr;
+    if (de != nullptr && atoi(de) != 0) {
+        if (dbg_buf == nullptr) cudaMallocManaged(&dbg_buf, 16 * 8 * sizeof(long long));
+        tp.dbg = dbg_buf;
+    }
     {
         ProfScope ps(st, PROF_ATTN_FWD, 4.0 * p.B * p.A * p.S * p.S * kHd, 1);
         attn_fwd_tc_kernel<<<grid, kThreadsTc, L.total, st>>>(tq, tkv, tp);
     }
     VB_CHECK_CUDA(cudaGetLastError());
+    if (tp.dbg != nullptr && ++dbg_calls == 3) {  // third call: warm
+        cudaStreamSynchronize(st);
+        printf("tc attention timeline (CTA 0, cycles): item: wait_S pass1 barrier pass2 wait_O epilogue | total\n");
+        for (int i = 0; i < 12; ++i) {
+            const long long* t = dbg_buf + i * 8;
+            printf("  item %2d: %6lld %6lld %6lld %6lld %6lld %6lld | %6lld\n", i, t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3],
+                   t[5] - t[4], t[6] - t[5], t[6] - t[0]);
+        }
+    }
     return 0;
 }
 
