@@ -43,8 +43,8 @@ int vb_profile_read(double* ms, double* work, int64_t* launches);
 /* ---- GEMM core (tcgen05.mma + TMA + TMEM) ------------------------------------------------ */
 /* epilogue selectors */
 #define VB_EPI_NONE 0
-#define VB_EPI_GELU 1  /* D = u (pre-activation), aux_out = gelu(u)      — M.py:56-61, 302-305 */
-#define VB_EPI_DGELU 2 /* D = acc * gelu'(aux_in)                        — backward of M.py:304 */
+#define VB_EPI_GELU 1  /* u = acc + bias: aux_out = gelu(u), D = gelu'(u)   — M.py:56-61, 302-305 */
+#define VB_EPI_DGELU 2 /* D = acc * aux_in  (aux_in = the gelu'(u) saved by VB_EPI_GELU) — backward of M.py:304 */
 
 typedef struct {
     /* D[M,N] = epilogue( sum_k A(m,k) * B(n,k) )
@@ -61,7 +61,7 @@ typedef struct {
     const float* bias;            /* fp32 [N] or NULL */
     const void* addend; int64_t ld_add; /* bf16 [M,N] added after bias/dropout (residual) or NULL */
     int32_t epilogue;             /* VB_EPI_* */
-    const void* aux_in;           /* VB_EPI_DGELU: u, bf16 [M,N] */
+    const void* aux_in;           /* VB_EPI_DGELU: gelu'(u), bf16 [M,N] */
     void* aux_out;                /* VB_EPI_GELU: gelu(u), bf16 [M,N] */
     int64_t ld_aux;
     /* inverted dropout on (acc + bias) before the addend — M.py:272, 317 (nn.Dropout) */
@@ -144,7 +144,7 @@ typedef struct {
     void* pre1;  /* [M, H]  attention.output.dense(ctx) (+dropout) + x          (M.py:271-273 before LN) */
     float* mean1; float* rstd1; /* [M] fp32 */
     void* x1;    /* [M, H]  attention output = LN(pre1) */
-    void* u;     /* [M, I]  intermediate.dense(x1) before gelu */
+    void* u;     /* [M, I]  gelu'(u), u = intermediate.dense(x1) — the derivative is what backward needs */
     void* g;     /* [M, I]  gelu(u) */
     void* pre2;  /* [M, H]  output.dense(g) (+dropout) + x1                      (M.py:316-318 before LN) */
     float* mean2; float* rstd2;

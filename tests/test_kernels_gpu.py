@@ -52,17 +52,16 @@ def test_gemm_gelu_and_dgelu():
     _gemm(_lib, L, st, A=A.data_ptr(), lda=K, B=B.data_ptr(), ldb=K, M=M, N=N, K=K, D=U.data_ptr(), ldd=N,
           bias=bias.data_ptr(), epilogue=_lib.VB_EPI_GELU, aux_out=G.data_ptr(), ld_aux=N)
     torch.cuda.synchronize()
-    u = A.float() @ B.float().t() + bias
-    assert _rel(U, u) < BF16_TOL
-    assert _rel(G, torch.nn.functional.gelu(u)) < BF16_TOL
-    Ub = torch.randn(M, N, device=dev).bfloat16()
+    u = (A.float() @ B.float().t() + bias).requires_grad_(True)
+    g = torch.nn.functional.gelu(u)
+    (gp,) = torch.autograd.grad(g.sum(), u)
+    assert _rel(G, g) < BF16_TOL        # aux_out = gelu(u)
+    assert _rel(U, gp) < BF16_TOL       # D = gelu'(u), saved for the backward
     D = torch.zeros_like(U)
     _gemm(_lib, L, st, A=A.data_ptr(), lda=K, B=B.data_ptr(), ldb=K, M=M, N=N, K=K, D=D.data_ptr(), ldd=N,
-          epilogue=_lib.VB_EPI_DGELU, aux_in=Ub.data_ptr(), ld_aux=N)
+          epilogue=_lib.VB_EPI_DGELU, aux_in=U.data_ptr(), ld_aux=N)
     torch.cuda.synchronize()
-    uu = Ub.float().requires_grad_(True)
-    (gp,) = torch.autograd.grad(torch.nn.functional.gelu(uu).sum(), uu)
-    assert _rel(D, (A.float() @ B.float().t()) * gp) < BF16_TOL
+    assert _rel(D, (A.float() @ B.float().t()) * U.float()) < BF16_TOL
 
 
 def test_gemm_dgrad_and_wgrad():

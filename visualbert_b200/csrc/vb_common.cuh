@@ -110,6 +110,15 @@ __device__ __forceinline__ float gelu_fwd(float x) {
     const float hx = 0.5f * x, ha = fabsf(hx);
     return fmaf(-ha, q, hx + ha);  // 0.5 x + 0.5 |x| (1 - q)
 }
+// gelu(x) and d/dx gelu(x) = Phi(x) + x phi(x) from the same exp / rcp (the FFN-up epilogue stores both, so the
+// backward epilogue is a single multiply)
+__device__ __forceinline__ void gelu_fwd_bwd(float x, float& g, float& gp) {
+    float e;
+    const float q = erfc_abs_sqrt2(x, e);
+    const float cdf = 0.5f + copysignf(fmaf(-0.5f, q, 0.5f), x);
+    g = x * cdf;
+    gp = fmaf(x * e, 0.3989422804014327f, cdf);
+}
 // d/dx gelu(x) = 0.5 (1 + erf(x/√2)) + x φ(x),  φ(x) = exp(-x²/2)/√(2π)
 __device__ __forceinline__ float gelu_bwd(float x) {
     float e;

@@ -193,16 +193,17 @@ __device__ __forceinline__ void epilogue16(const GemmParams& p, int row, int col
         }
         bf16* d = reinterpret_cast<bf16*>(p.D) + static_cast<long long>(row) * p.ldd + col;
         if (p.epilogue == VB_EPI_GELU) {
-            // D <- u (kept for backward), aux_out <- gelu(u) (operand of the next GEMM)
-            store16_bf16(d, x);
+            // aux_out <- gelu(u) (operand of the next GEMM), D <- gelu'(u) (all the backward needs of u)
+            float gp[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) x[i] = gelu_fwd(x[i]);
+            for (int i = 0; i < 16; ++i) gelu_fwd_bwd(x[i], x[i], gp[i]);
+            store16_bf16(d, gp);
             d = p.aux_out + static_cast<long long>(row) * p.ld_aux + col;
         } else if (p.epilogue == VB_EPI_DGELU) {
-            float u[16];
-            load16_bf16(p.aux_in + static_cast<long long>(row) * p.ld_aux + col, u);
+            float gp[16];
+            load16_bf16(p.aux_in + static_cast<long long>(row) * p.ld_aux + col, gp);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) x[i] *= gelu_bwd(u[i]);
+            for (int i = 0; i < 16; ++i) x[i] *= gp[i];
         }
         store16_bf16(d, x);
     }
