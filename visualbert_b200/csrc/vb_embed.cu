@@ -191,14 +191,27 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __rest
     }
 }
 
-// out[N] += column sums of x[M, N] (bf16). block = 32 x 8: x -> 8-column chunk, y -> row phase.
+// out[N] += column sums of x[M, N] (bf16). block = 32 x 8: x -> 8-column chunk, y -> row phase; four rows per
+// iteration so every thread keeps 4 x 16 B loads in flight (the kernel is pure HBM streaming).
 __global__ void __launch_bounds__(256)
 colsum_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ out, int M, int N) {
     __shared__ float red[8][32][9];
     const int ch = blockIdx.x * 32 + threadIdx.x;
     float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (ch * 8 < N) {
-        for (int r = blockIdx.y * 8 + threadIdx.y; r < M; r += gridDim.y * 8) {
+        const int stride = gridDim.y * 8;
+        int r = blockIdx.y * 8 + threadIdx.y;
+        for (; r + 3 * stride < M; r += 4 * stride) {
+            uint4 u[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) u[j] = ldg_v4(x + static_cast<long long>(r + j * stride) * ld + ch * 8);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 x0 = unpack_bf16x2(u[j].x), x1 = unpack_bf16x2(u[j].y), x2 = unpack_bf16x2(u[j].z), x3 = unpack_bf16x2(u[j].w);
+                a[0] += x0.x; a[1] += x0.y; a[2] += x1.x; a[3] += x1.y; a[4] += x2.x; a[5] += x2.y; a[6] += x3.x; a[7] += x3.y;
+            }
+        }
+        for (; r < M; r += stride) {
             const uint4 u = ldg_v4(x + static_cast<long long>(r) * ld + ch * 8);
             const float2 x0 = unpack_bf16x2(u.x), x1 = unpack_bf16x2(u.y), x2 = unpack_bf16x2(u.z), x3 = unpack_bf16x2(u.w);
             a[0] += x0.x; a[1] += x0.y; a[2] += x1.x; a[3] += x1.y; a[4] += x2.x; a[5] += x2.y; a[6] += x3.x; a[7] += x3.y;
@@ -296,7 +309,7 @@ int cast_bf16_f32(const void* src, float* dst, long long n, cudaStream_t st) {
 int colsum(const void* x, long long ld, float* out, int M, int N, cudaStream_t st) {
     VB_REQUIRE(N % 8 == 0 && M > 0, "colsum: bad shape");
     const int gx = (N / 8 + 31) / 32;
-    int gy = (num_sms() * 4) / gx;
+    int gy = (num_sms() * 6) / gx;
     if (gy < 1) gy = 1;
     if (gy > (M + 7) / 8) gy = (M + 7) / 8;
     {
