@@ -116,6 +116,8 @@ def run_case(name):
         for tag, (M, N, K, kw) in {
             "qkv_fwd": (41984, 2304, 768, {}),
             "ffn_up_gelu": (41984, 3072, 768, {"gelu": True}),
+            "ffn_up_dual_nomath": (41984, 3072, 768, {"gelu": True, "epi": 3}),
+            "ffn_up_plain": (41984, 3072, 768, {}),
             "ffn_down": (41984, 768, 3072, {}),
             "dgrad_ffn_up": (41984, 768, 3072, {"dgrad": True}),
             "wgrad_ffn_up": (3072, 768, 41984, {"wgrad": True}),
@@ -139,7 +141,7 @@ def run_case(name):
                 if kw.get("gelu"):
                     G = torch.zeros_like(D)
                     bias = torch.randn(N, device=dev)
-                    args.update(epilogue=_lib.VB_EPI_GELU, aux_out=G.data_ptr(), ld_aux=N, bias=bias.data_ptr())
+                    args.update(epilogue=kw.get("epi", _lib.VB_EPI_GELU), aux_out=G.data_ptr(), ld_aux=N, bias=bias.data_ptr())
             for _ in range(3):
                 call(**args)
             torch.cuda.synchronize()

@@ -199,6 +199,9 @@ __device__ __forceinline__ void epilogue16(const GemmParams& p, int row, int col
             for (int i = 0; i < 16; ++i) gelu_fwd_bwd(x[i], x[i], gp[i]);
             store16_bf16(d, gp);
             d = p.aux_out + static_cast<long long>(row) * p.ld_aux + col;
+        } else if (p.epilogue == 3) {  // debug/tuning only: two stores, no GELU math
+            store16_bf16(d, x);
+            d = p.aux_out + static_cast<long long>(row) * p.ld_aux + col;
         } else if (p.epilogue == VB_EPI_DGELU) {
             float gp[16];
             load16_bf16(p.aux_in + static_cast<long long>(row) * p.ld_aux + col, gp);
@@ -690,7 +693,7 @@ int gemm(const vb_gemm_args& a, cudaStream_t st) {
     VB_REQUIRE(a.ldd % 16 == 0 && (reinterpret_cast<uintptr_t>(a.D) & 31) == 0, "vb_gemm: D must be 32-byte aligned with ldd a multiple of 16");
     VB_REQUIRE(!a.addend || (a.ld_add % 16 == 0 && (reinterpret_cast<uintptr_t>(a.addend) & 31) == 0), "vb_gemm: addend must be 32-byte aligned with ld a multiple of 16");
     VB_REQUIRE((!a.aux_in && !a.aux_out) || a.ld_aux % 16 == 0, "vb_gemm: ld_aux must be a multiple of 16");
-    VB_REQUIRE(a.epilogue == VB_EPI_NONE || a.epilogue == VB_EPI_GELU || a.epilogue == VB_EPI_DGELU,
+    VB_REQUIRE(a.epilogue == VB_EPI_NONE || a.epilogue == VB_EPI_GELU || a.epilogue == VB_EPI_DGELU || a.epilogue == 3,
                "vb_gemm: unknown epilogue %d", a.epilogue);
     VB_REQUIRE(a.epilogue != VB_EPI_GELU || a.aux_out, "vb_gemm: GELU epilogue needs aux_out");
     VB_REQUIRE(a.epilogue != VB_EPI_DGELU || a.aux_in, "vb_gemm: DGELU epilogue needs aux_in");

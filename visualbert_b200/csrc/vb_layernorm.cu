@@ -100,7 +100,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 __device__ __forceinline__ int slot(int a, int h, int ch, int chunks) { return (a * 2 + h) * chunks + ch; }
 
 template <int NC>
-__global__ void __launch_bounds__(kLnWarps * 32, 2)
+__global__ void __launch_bounds__(kLnWarps * 32, 3)
 ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ gamma, bf16* __restrict__ dx,
               bf16* __restrict__ dx_drop, float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -120,107 +120,77 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
     __syncthreads();
 
     const float invH = 1.0f / H;
-    // Two rows per iteration: 4*NC 16-byte loads in flight per lane, and the shared-memory accumulators are
-    // read-modify-written once per row PAIR (the two rows' contributions are summed in registers first).
-    const int rstride = gridDim.x * kLnWarps;
-    for (int row0 = blockIdx.x * kLnWarps + warp; row0 < rows; row0 += 2 * rstride) {
-        const int row1 = row0 + rstride;
-        const bool has1 = row1 < rows;
-        uint4 ux[2][NC], ud[2][NC];
+    for (int row = blockIdx.x * kLnWarps + warp; row < rows; row += gridDim.x * kLnWarps) {
+        uint4 ux[NC], ud[NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             const int ch = lane + c * 32;
             if (ch < chunks) {
-                ux[0][c] = ldg_v4(x + static_cast<long long>(row0) * H + ch * 8);
-                ud[0][c] = ldg_v4(dy + static_cast<long long>(row0) * H + ch * 8);
-                if (has1) {
-                    ux[1][c] = ldg_v4(x + static_cast<long long>(row1) * H + ch * 8);
-                    ud[1][c] = ldg_v4(dy + static_cast<long long>(row1) * H + ch * 8);
-                }
+                ux[c] = ldg_v4(x + static_cast<long long>(row) * H + ch * 8);
+                ud[c] = ldg_v4(dy + static_cast<long long>(row) * H + ch * 8);
             }
         }
-        float mu[2], rs[2], c1[2], c2[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            if (k == 1 && !has1) break;
-            const int row = k == 0 ? row0 : row1;
-            mu[k] = mean[row];
-            rs[k] = rstd[row];
-            float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                const int ch = lane + c * 32;
-                if (ch < chunks) {
-                    float xv[8], dv[8];
-                    unpack8(ux[k][c], xv);
-                    unpack8(ud[k][c], dv);
-                    if (in_scale != 0.f) {  // dy is the gradient of dropout(LN(x)): re-apply the keep mask
-                        const unsigned long long e8 = (static_cast<unsigned long long>(row) * static_cast<unsigned>(H) + ch * 8) >> 3;
-                        const uint32_t keep = dropout_keep8(drop_seed, in_stream, e8, in_thresh16);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) dv[i] = ((keep >> i) & 1u) ? dv[i] * in_scale : 0.f;
-                    }
-                    const float4 g0 = sgam[ch], g1 = sgam[chunks + ch];
-                    const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float g = dv[i] * gm[i];
-                        s1 += g;
-                        s2 += g * ((xv[i] - mu[k]) * rs[k]);
-                    }
-                }
-            }
-            c1[k] = warp_sum(s1) * invH;
-            c2[k] = warp_sum(s2) * invH;
-        }
+        const float mu = mean[row], rs = rstd[row];
+        float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             const int ch = lane + c * 32;
             if (ch < chunks) {
-                float ag[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, ab[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f},
-                      ad[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                float xv[8], dv[8];
+                unpack8(ux[c], xv);
+                unpack8(ud[c], dv);
+                if (in_scale != 0.f) {  // dy is the gradient of dropout(LN(x)): re-apply the keep mask
+                    const unsigned long long e8 = (static_cast<unsigned long long>(row) * static_cast<unsigned>(H) + ch * 8) >> 3;
+                    const uint32_t keep = dropout_keep8(drop_seed, in_stream, e8, in_thresh16);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dv[i] = ((keep >> i) & 1u) ? dv[i] * in_scale : 0.f;
+                }
                 const float4 g0 = sgam[ch], g1 = sgam[chunks + ch];
                 const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    if (k == 1 && !has1) break;
-                    const int row = k == 0 ? row0 : row1;
-                    float xv[8], dv[8], o[8];
-                    unpack8(ux[k][c], xv);
-                    unpack8(ud[k][c], dv);
-                    if (in_scale != 0.f) {
-                        const unsigned long long e8 = (static_cast<unsigned long long>(row) * static_cast<unsigned>(H) + ch * 8) >> 3;
-                        const uint32_t keep = dropout_keep8(drop_seed, in_stream, e8, in_thresh16);
+                for (int i = 0; i < 8; ++i) {
+                    const float g = dv[i] * gm[i];
+                    s1 += g;
+                    s2 += g * ((xv[i] - mu) * rs);
+                }
+            }
+        }
+        const float c1 = warp_sum(s1) * invH, c2 = warp_sum(s2) * invH;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) dv[i] = ((keep >> i) & 1u) ? dv[i] * in_scale : 0.f;
-                    }
+        for (int c = 0; c < NC; ++c) {
+            const int ch = lane + c * 32;
+            if (ch < chunks) {
+                float xv[8], dv[8], o[8];
+                unpack8(ux[c], xv);
+                unpack8(ud[c], dv);
+                if (in_scale != 0.f) {
+                    const unsigned long long e8 = (static_cast<unsigned long long>(row) * static_cast<unsigned>(H) + ch * 8) >> 3;
+                    const uint32_t keep = dropout_keep8(drop_seed, in_stream, e8, in_thresh16);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        xv[i] = (xv[i] - mu[k]) * rs[k];  // xhat
-                        o[i] = rs[k] * (dv[i] * gm[i] - c1[k] - xv[i] * c2[k]);
-                    }
-                    stg_v4(dx + static_cast<long long>(row) * H + ch * 8, pack8(o));
-                    if (dx_drop != nullptr) {
-                        const unsigned long long e8 = (static_cast<unsigned long long>(row) * static_cast<unsigned>(H) + ch * 8) >> 3;
-                        const uint32_t keep = dropout_keep8(drop_seed, drop_stream, e8, drop_thresh16);
+                    for (int i = 0; i < 8; ++i) dv[i] = ((keep >> i) & 1u) ? dv[i] * in_scale : 0.f;
+                }
+                const float4 g0 = sgam[ch], g1 = sgam[chunks + ch];
+                const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) o[i] = ((keep >> i) & 1u) ? o[i] * drop_scale : 0.f;
-                        stg_v4(dx_drop + static_cast<long long>(row) * H + ch * 8, pack8(o));
-                    }
+                for (int i = 0; i < 8; ++i) {
+                    xv[i] = (xv[i] - mu) * rs;  // xhat
+                    o[i] = rs * (dv[i] * gm[i] - c1 - xv[i] * c2);
+                }
+                stg_v4(dx + static_cast<long long>(row) * H + ch * 8, pack8(o));
+                if (dx_drop != nullptr) {
+                    const unsigned long long e8 = (static_cast<unsigned long long>(row) * static_cast<unsigned>(H) + ch * 8) >> 3;
+                    const uint32_t keep = dropout_keep8(drop_seed, drop_stream, e8, drop_thresh16);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        ag[i] += dv[i] * xv[i];
-                        ab[i] += dv[i];
-                        ad[i] += o[i];
-                    }
+                    for (int i = 0; i < 8; ++i) o[i] = ((keep >> i) & 1u) ? o[i] * drop_scale : 0.f;
+                    stg_v4(dx_drop + static_cast<long long>(row) * H + ch * 8, pack8(o));
                 }
                 float4 a;
-                a = acc[slot(0, 0, ch, chunks)]; a.x += ag[0]; a.y += ag[1]; a.z += ag[2]; a.w += ag[3]; acc[slot(0, 0, ch, chunks)] = a;
-                a = acc[slot(0, 1, ch, chunks)]; a.x += ag[4]; a.y += ag[5]; a.z += ag[6]; a.w += ag[7]; acc[slot(0, 1, ch, chunks)] = a;
-                a = acc[slot(1, 0, ch, chunks)]; a.x += ab[0]; a.y += ab[1]; a.z += ab[2]; a.w += ab[3]; acc[slot(1, 0, ch, chunks)] = a;
-                a = acc[slot(1, 1, ch, chunks)]; a.x += ab[4]; a.y += ab[5]; a.z += ab[6]; a.w += ab[7]; acc[slot(1, 1, ch, chunks)] = a;
-                a = acc[slot(2, 0, ch, chunks)]; a.x += ad[0]; a.y += ad[1]; a.z += ad[2]; a.w += ad[3]; acc[slot(2, 0, ch, chunks)] = a;
-                a = acc[slot(2, 1, ch, chunks)]; a.x += ad[4]; a.y += ad[5]; a.z += ad[6]; a.w += ad[7]; acc[slot(2, 1, ch, chunks)] = a;
+                a = acc[slot(0, 0, ch, chunks)]; a.x += dv[0] * xv[0]; a.y += dv[1] * xv[1]; a.z += dv[2] * xv[2]; a.w += dv[3] * xv[3]; acc[slot(0, 0, ch, chunks)] = a;
+                a = acc[slot(0, 1, ch, chunks)]; a.x += dv[4] * xv[4]; a.y += dv[5] * xv[5]; a.z += dv[6] * xv[6]; a.w += dv[7] * xv[7]; acc[slot(0, 1, ch, chunks)] = a;
+                a = acc[slot(1, 0, ch, chunks)]; a.x += dv[0]; a.y += dv[1]; a.z += dv[2]; a.w += dv[3]; acc[slot(1, 0, ch, chunks)] = a;
+                a = acc[slot(1, 1, ch, chunks)]; a.x += dv[4]; a.y += dv[5]; a.z += dv[6]; a.w += dv[7]; acc[slot(1, 1, ch, chunks)] = a;
+                a = acc[slot(2, 0, ch, chunks)]; a.x += o[0]; a.y += o[1]; a.z += o[2]; a.w += o[3]; acc[slot(2, 0, ch, chunks)] = a;
+                a = acc[slot(2, 1, ch, chunks)]; a.x += o[4]; a.y += o[5]; a.z += o[6]; a.w += o[7]; acc[slot(2, 1, ch, chunks)] = a;
             }
         }
     }
@@ -267,8 +237,8 @@ int ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, 
     VB_REQUIRE(rows > 0, "layernorm backward: no rows");
     VB_REQUIRE((dropout_p > 0.f) == (dx_drop != nullptr), "layernorm backward: dx_drop iff dropout_p > 0");
     const int nc = (H / 8 + 31) / 32;
-    int grid = num_sms() * 2;
-    const int need = (rows + 2 * kLnWarps - 1) / (2 * kLnWarps);
+    int grid = num_sms() * 3;
+    const int need = (rows + kLnWarps - 1) / kLnWarps;
     if (grid > need) grid = need;
     const float scale = dropout_p > 0.f ? 1.0f / (1.0f - dropout_p) : 0.f;
     const unsigned th = static_cast<unsigned>(dropout_p * 65536.0f + 0.5f);
