@@ -107,9 +107,9 @@ def run_case(name):
         dropped = (D1 == 0) & (D0 != 0)
         frac = dropped.float().mean().item()
         kept = ~dropped
-        rel = report(D1[kept], (D0.float() / 0.9)[kept], "dropout:kept")
+        rel = report(D1[kept], (D0.float() / (1 - 26 / 256))[kept], "dropout:kept")
         print(f"  dropout deterministic={same} drop_frac={frac:.4f} (expect 0.1000)")
-        if not same or abs(frac - 0.1) > 0.005:
+        if not same or abs(frac - 26 / 256) > 0.005:
             rel = 1.0
     elif name == "perf":
         res = {}

@@ -158,8 +158,9 @@ int embed_fwd_api(const vb_embed_desc* d, void* y, const vb_embed_acts* s, cudaS
     p.vocab = d->vocab; p.max_pos = d->max_pos; p.n_types = d->n_types;
     p.eps = d->eps;
     if (d->dropout > 0.f) {
-        p.drop_scale = 1.f / (1.f - d->dropout);
-        p.drop_thresh16 = static_cast<unsigned>(d->dropout * 65536.f + 0.5f);
+        const DropQ q = dropout_quantise(d->dropout);
+        p.drop_scale = q.scale;
+        p.drop_thresh16 = q.thr8;
         p.drop_seed = d->seed;
         p.drop_stream = kEmbedDropStream;
     }

@@ -142,20 +142,28 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
 __device__ __forceinline__ uint32_t dropout_key(uint64_t seed, uint32_t stream) {
     return mix32(static_cast<uint32_t>(seed) ^ mix32(static_cast<uint32_t>(seed >> 32) + 0x9E3779B9u * (stream + 1u)));
 }
+// Hidden-state dropout quantises the drop probability to n/256 (0.1 -> 26/256 = 0.1016) and scales survivors by
+// 256/(256-n), so E[dropout(x)] = x exactly while one hash serves 4 elements and the threshold test is a single
+// SIMD byte compare. Host side: dropout_quantise().
+struct DropQ { unsigned thr8; float scale; };
+inline DropQ dropout_quantise(float p) {
+    DropQ q;
+    unsigned n = static_cast<unsigned>(p * 256.0f + 0.5f);
+    if (n > 255u) n = 255u;
+    q.thr8 = n;
+    q.scale = p > 0.f ? 256.0f / (256.0f - static_cast<float>(n)) : 0.f;
+    return q;
+}
 // Keep-mask bits for the 8 consecutive elements starting at flat element index `elem8 * 8`.
-// Each element consumes 16 random bits; kept iff bits >= thresh16 (thresh16 = round(p * 65536)).
-__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint32_t stream, uint64_t elem8,
-                                                  uint32_t thresh16) {
-    const uint32_t key = dropout_key(seed, stream) ^ (static_cast<uint32_t>(elem8 >> 30) * 0x27d4eb2fu);
-    const uint32_t base = static_cast<uint32_t>(elem8) << 2;
-    uint32_t m = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint32_t r = mix32((base + i) ^ key);
-        m |= static_cast<uint32_t>((r & 0xffffu) >= thresh16) << (2 * i);
-        m |= static_cast<uint32_t>((r >> 16) >= thresh16) << (2 * i + 1);
-    }
-    return m;
+// Each element consumes 8 random bits; kept iff bits >= thr8.
+__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint32_t stream, uint64_t elem8, uint32_t thr8) {
+    const uint32_t key = dropout_key(seed, stream) ^ (static_cast<uint32_t>(elem8 >> 31) * 0x27d4eb2fu);
+    const uint32_t base = static_cast<uint32_t>(elem8) << 1;
+    const uint32_t t4 = thr8 * 0x01010101u;
+    // __vcmpgeu4: per-byte (a >= b) ? 0xff : 0x00; the multiply gathers the 4 byte LSBs into one nibble
+    const uint32_t m0 = __vcmpgeu4(mix32(base ^ key), t4) & 0x01010101u;
+    const uint32_t m1 = __vcmpgeu4(mix32((base + 1u) ^ key), t4) & 0x01010101u;
+    return ((m0 * 0x01020408u) >> 24) | (((m1 * 0x01020408u) >> 24) << 4);
 }
 
 // ---------------------------------------------------------------------------------------------

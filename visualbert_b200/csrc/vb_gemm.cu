@@ -99,8 +99,8 @@ struct GemmParams {
     int epilogue;
     const bf16* aux_in;
     bf16* aux_out; long long ld_aux;
-    float drop_scale;        // 1/(1-p), 0 => dropout off
-    unsigned drop_thresh16;  // round(p * 65536)
+    float drop_scale;        // 256/(256-n), 0 => dropout off
+    unsigned drop_thresh16;  // n = round(p * 256): 8-bit keep threshold (see dropout_quantise)
     unsigned long long drop_seed;
     unsigned drop_stream;
 };
@@ -716,8 +716,9 @@ int gemm(const vb_gemm_args& a, cudaStream_t st) {
     p.aux_out = static_cast<bf16*>(a.aux_out);
     p.ld_aux = a.ld_aux;
     if (a.dropout_p > 0.0f) {
-        p.drop_scale = 1.0f / (1.0f - a.dropout_p);
-        p.drop_thresh16 = static_cast<unsigned>(a.dropout_p * 65536.0f + 0.5f);
+        const DropQ q = dropout_quantise(a.dropout_p);
+        p.drop_scale = q.scale;
+        p.drop_thresh16 = q.thr8;
         p.drop_seed = a.dropout_seed;
         p.drop_stream = a.dropout_stream;
     }

@@ -240,10 +240,9 @@ int ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, 
     int grid = num_sms() * 3;
     const int need = (rows + kLnWarps - 1) / kLnWarps;
     if (grid > need) grid = need;
-    const float scale = dropout_p > 0.f ? 1.0f / (1.0f - dropout_p) : 0.f;
-    const unsigned th = static_cast<unsigned>(dropout_p * 65536.0f + 0.5f);
-    const float in_scale = in_dropout_p > 0.f ? 1.0f / (1.0f - in_dropout_p) : 0.f;
-    const unsigned in_th = static_cast<unsigned>(in_dropout_p * 65536.0f + 0.5f);
+    const DropQ dq = dropout_quantise(dropout_p), iq = dropout_quantise(in_dropout_p);
+    const float scale = dq.scale, in_scale = iq.scale;
+    const unsigned th = dq.thr8, in_th = iq.thr8;
     const size_t smem = static_cast<size_t>(2 * (H / 8) + kLnWarps * 6 * (H / 8)) * sizeof(float4);
     static bool configured = false;
     if (!configured) {
