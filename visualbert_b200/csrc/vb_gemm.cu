@@ -161,8 +161,11 @@ __device__ __forceinline__ void store16_bf16(bf16* p, const float (&f)[16]) {
 }
 
 // `sbias` points at the 16 staged bias values of these columns in shared memory (or nullptr).
+// `ex` holds the 16 bf16 of the residual (addend) or of gelu'(u) (aux_in) for these columns, prefetched by the
+// caller one chunk ahead so the row-strided global load never sits on the critical path.
 template <bool OUT_F32>
-__device__ __forceinline__ void epilogue16(const GemmParams& p, int row, int col, const float* sbias, float (&x)[16]) {
+__device__ __forceinline__ void epilogue16(const GemmParams& p, int row, int col, const float* sbias, const uint32_t (&ex)[8],
+                                           float (&x)[16]) {
     if (sbias != nullptr) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -186,10 +189,12 @@ __device__ __forceinline__ void epilogue16(const GemmParams& p, int row, int col
             }
         }
         if (p.addend != nullptr) {
-            float a[16];
-            load16_bf16(p.addend + static_cast<long long>(row) * p.ld_add + col, a);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) x[i] += a[i];
+            for (int i = 0; i < 8; ++i) {
+                const float2 t = unpack_bf16x2(ex[i]);
+                x[2 * i] += t.x;
+                x[2 * i + 1] += t.y;
+            }
         }
         bf16* d = reinterpret_cast<bf16*>(p.D) + static_cast<long long>(row) * p.ldd + col;
         if (p.epilogue == VB_EPI_GELU) {
@@ -203,10 +208,12 @@ __device__ __forceinline__ void epilogue16(const GemmParams& p, int row, int col
             store16_bf16(d, x);
             d = p.aux_out + static_cast<long long>(row) * p.ld_aux + col;
         } else if (p.epilogue == VB_EPI_DGELU) {
-            float gp[16];
-            load16_bf16(p.aux_in + static_cast<long long>(row) * p.ld_aux + col, gp);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) x[i] *= gp[i];
+            for (int i = 0; i < 8; ++i) {
+                const float2 t = unpack_bf16x2(ex[i]);
+                x[2 * i] *= t.x;
+                x[2 * i + 1] *= t.y;
+            }
         }
         store16_bf16(d, x);
     }
@@ -358,17 +365,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                     half * (BLOCK_N / 2);
             // software pipeline: the TMEM load of chunk k+1 is in flight while chunk k is processed
             uint32_t v[2][16];
+            uint32_t ex[2][8];
+            // residual / gelu' operand of this thread's row: one 32-byte load per 16-column chunk, issued a chunk ahead
+            const bf16* exp_ = nullptr;
+            if constexpr (!OUT_F32) {
+                if (p.addend != nullptr) exp_ = p.addend + static_cast<long long>(row) * p.ld_add;
+                else if (p.epilogue == VB_EPI_DGELU) exp_ = p.aux_in + static_cast<long long>(row) * p.ld_aux;
+                if (row >= p.M) exp_ = nullptr;
+            }
             tmem_ld_32x32b_x16(taddr0, v[0]);
+            if (exp_ != nullptr && col0 < p.N) ldg_v8(exp_ + col0, ex[0]);
 #pragma unroll
             for (int k = 0; k < NCH; ++k) {
                 tmem_ld_wait();
-                if (k + 1 < NCH) tmem_ld_32x32b_x16(taddr0 + (k + 1) * 16, v[(k + 1) & 1]);
+                if (k + 1 < NCH) {
+                    tmem_ld_32x32b_x16(taddr0 + (k + 1) * 16, v[(k + 1) & 1]);
+                    if (exp_ != nullptr && col0 + (k + 1) * 16 < p.N) ldg_v8(exp_ + col0 + (k + 1) * 16, ex[(k + 1) & 1]);
+                }
                 const int col = col0 + k * 16;
                 if (row < p.M && col < p.N) {
                     float x[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[k & 1][i]);
-                    epilogue16<OUT_F32>(p, row, col, has_bias ? sb + half * (BLOCK_N / 2) + k * 16 : nullptr, x);
+                    epilogue16<OUT_F32>(p, row, col, has_bias ? sb + half * (BLOCK_N / 2) + k * 16 : nullptr, ex[k & 1], x);
                 }
             }
             tcgen05_fence_before();
@@ -560,17 +579,29 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const int col0 = tc.n_blk * BLOCK_N + half * (BLOCK_N / 2);
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + half * (BLOCK_N / 2);
             uint32_t v[2][16];
+            uint32_t ex[2][8];
+            // residual / gelu' operand of this thread's row: one 32-byte load per 16-column chunk, issued a chunk ahead
+            const bf16* exp_ = nullptr;
+            if constexpr (!OUT_F32) {
+                if (p.addend != nullptr) exp_ = p.addend + static_cast<long long>(row) * p.ld_add;
+                else if (p.epilogue == VB_EPI_DGELU) exp_ = p.aux_in + static_cast<long long>(row) * p.ld_aux;
+                if (row >= p.M) exp_ = nullptr;
+            }
             tmem_ld_32x32b_x16(taddr0, v[0]);
+            if (exp_ != nullptr && col0 < p.N) ldg_v8(exp_ + col0, ex[0]);
 #pragma unroll
             for (int k = 0; k < NCH; ++k) {
                 tmem_ld_wait();
-                if (k + 1 < NCH) tmem_ld_32x32b_x16(taddr0 + (k + 1) * 16, v[(k + 1) & 1]);
+                if (k + 1 < NCH) {
+                    tmem_ld_32x32b_x16(taddr0 + (k + 1) * 16, v[(k + 1) & 1]);
+                    if (exp_ != nullptr && col0 + (k + 1) * 16 < p.N) ldg_v8(exp_ + col0 + (k + 1) * 16, ex[(k + 1) & 1]);
+                }
                 const int col = col0 + k * 16;
                 if (row < p.M && col < p.N) {
                     float x[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[k & 1][i]);
-                    epilogue16<OUT_F32>(p, row, col, has_bias ? sb + half * (BLOCK_N / 2) + k * 16 : nullptr, x);
+                    epilogue16<OUT_F32>(p, row, col, has_bias ? sb + half * (BLOCK_N / 2) + k * 16 : nullptr, ex[k & 1], x);
                 }
             }
             tcgen05_fence_before();
@@ -693,6 +724,8 @@ int gemm(const vb_gemm_args& a, cudaStream_t st) {
     VB_REQUIRE(a.ldd % 16 == 0 && (reinterpret_cast<uintptr_t>(a.D) & 31) == 0, "vb_gemm: D must be 32-byte aligned with ldd a multiple of 16");
     VB_REQUIRE(!a.addend || (a.ld_add % 16 == 0 && (reinterpret_cast<uintptr_t>(a.addend) & 31) == 0), "vb_gemm: addend must be 32-byte aligned with ld a multiple of 16");
     VB_REQUIRE((!a.aux_in && !a.aux_out) || a.ld_aux % 16 == 0, "vb_gemm: ld_aux must be a multiple of 16");
+    VB_REQUIRE((reinterpret_cast<uintptr_t>(a.aux_in) & 31) == 0 && (reinterpret_cast<uintptr_t>(a.aux_out) & 31) == 0,
+               "vb_gemm: aux_in / aux_out must be 32-byte aligned");
     VB_REQUIRE(a.epilogue == VB_EPI_NONE || a.epilogue == VB_EPI_GELU || a.epilogue == VB_EPI_DGELU || a.epilogue == 3,
                "vb_gemm: unknown epilogue %d", a.epilogue);
     VB_REQUIRE(a.epilogue != VB_EPI_GELU || a.aux_out, "vb_gemm: GELU epilogue needs aux_out");
