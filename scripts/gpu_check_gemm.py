@@ -118,6 +118,11 @@ def run_case(name):
             "ffn_up_gelu": (41984, 3072, 768, {"gelu": True}),
             "ffn_up_dual_nomath": (41984, 3072, 768, {"gelu": True, "epi": 3}),
             "ffn_up_plain": (41984, 3072, 768, {}),
+            "attn_out_plain": (41984, 768, 768, {}),
+            "attn_out_bias_add": (41984, 768, 768, {"add": True}),
+            "attn_out_bias_add_drop": (41984, 768, 768, {"add": True, "drop": True}),
+            "ffn_down_bias_add_drop": (41984, 768, 3072, {"add": True, "drop": True}),
+            "qkv_bias": (41984, 2304, 768, {"bias": True}),
             "ffn_down": (41984, 768, 3072, {}),
             "dgrad_ffn_up": (41984, 768, 3072, {"dgrad": True}),
             "wgrad_ffn_up": (3072, 768, 41984, {"wgrad": True}),
@@ -138,6 +143,14 @@ def run_case(name):
                 A = rnd(M, K); B = rnd(N, K)
                 D = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
                 args = dict(A=A.data_ptr(), lda=K, B=B.data_ptr(), ldb=K, M=M, N=N, K=K, D=D.data_ptr(), ldd=N)
+                if kw.get("add") or kw.get("bias"):
+                    bias = torch.randn(N, device=dev)
+                    args.update(bias=bias.data_ptr())
+                if kw.get("add"):
+                    R = rnd(M, N)
+                    args.update(addend=R.data_ptr(), ld_add=N)
+                if kw.get("drop"):
+                    args.update(dropout_p=0.1, dropout_seed=5, dropout_stream=1)
                 if kw.get("gelu"):
                     G = torch.zeros_like(D)
                     bias = torch.randn(N, device=dev)

@@ -357,37 +357,41 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 named_bar_sync(1, kEpiWarps * 32);
             }
-            mbar_wait(tfull_bar(acc), acc_phase);
-            tcgen05_fence_after();
             const int row = tc.m_blk * BLOCK_M + q * 32 + lane;
             const int col0 = tc.n_blk * BLOCK_N + half * (BLOCK_N / 2);
-            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N +
-                                    half * (BLOCK_N / 2);
-            // software pipeline: the TMEM load of chunk k+1 is in flight while chunk k is processed
-            uint32_t v[2][16];
-            uint32_t ex[2][8];
-            // residual / gelu' operand of this thread's row: one 32-byte load per 16-column chunk, issued a chunk ahead
+            // Residual / gelu' operand of this thread's row: one 32-byte load per 16-column chunk. The loads are
+            // row-strided DRAM accesses (~1 us each under load), so kExAhead of them are kept in flight and the
+            // first batch is issued BEFORE waiting for the accumulator.
+            constexpr int kExAhead = 4;
+            uint32_t ex[kExAhead][8];
             const bf16* exp_ = nullptr;
             if constexpr (!OUT_F32) {
                 if (p.addend != nullptr) exp_ = p.addend + static_cast<long long>(row) * p.ld_add;
                 else if (p.epilogue == VB_EPI_DGELU) exp_ = p.aux_in + static_cast<long long>(row) * p.ld_aux;
                 if (row >= p.M) exp_ = nullptr;
             }
+#pragma unroll
+            for (int k = 0; k < kExAhead; ++k)
+                if (exp_ != nullptr && col0 + k * 16 < p.N) ldg_v8(exp_ + col0 + k * 16, ex[k]);
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tcgen05_fence_after();
+            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N +
+                                    half * (BLOCK_N / 2);
+            // software pipeline: the TMEM load of chunk k+1 is in flight while chunk k is processed
+            uint32_t v[2][16];
             tmem_ld_32x32b_x16(taddr0, v[0]);
-            if (exp_ != nullptr && col0 < p.N) ldg_v8(exp_ + col0, ex[0]);
 #pragma unroll
             for (int k = 0; k < NCH; ++k) {
                 tmem_ld_wait();
-                if (k + 1 < NCH) {
-                    tmem_ld_32x32b_x16(taddr0 + (k + 1) * 16, v[(k + 1) & 1]);
-                    if (exp_ != nullptr && col0 + (k + 1) * 16 < p.N) ldg_v8(exp_ + col0 + (k + 1) * 16, ex[(k + 1) & 1]);
-                }
+                if (k + 1 < NCH) tmem_ld_32x32b_x16(taddr0 + (k + 1) * 16, v[(k + 1) & 1]);
+                if (k + kExAhead < NCH && exp_ != nullptr && col0 + (k + kExAhead) * 16 < p.N)
+                    ldg_v8(exp_ + col0 + (k + kExAhead) * 16, ex[(k + kExAhead) % kExAhead]);
                 const int col = col0 + k * 16;
                 if (row < p.M && col < p.N) {
                     float x[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[k & 1][i]);
-                    epilogue16<OUT_F32>(p, row, col, has_bias ? sb + half * (BLOCK_N / 2) + k * 16 : nullptr, ex[k & 1], x);
+                    epilogue16<OUT_F32>(p, row, col, has_bias ? sb + half * (BLOCK_N / 2) + k * 16 : nullptr, ex[k % kExAhead], x);
                 }
             }
             tcgen05_fence_before();
@@ -573,35 +577,39 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 }
                 named_bar_sync(1, kEpiWarps * 32);
             }
-            mbar_wait(tfull_bar(acc), acc_phase);
-            tcgen05_fence_after();
             const int row = tc.m_blk * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;
             const int col0 = tc.n_blk * BLOCK_N + half * (BLOCK_N / 2);
-            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + half * (BLOCK_N / 2);
-            uint32_t v[2][16];
-            uint32_t ex[2][8];
-            // residual / gelu' operand of this thread's row: one 32-byte load per 16-column chunk, issued a chunk ahead
+            // Residual / gelu' operand of this thread's row: one 32-byte load per 16-column chunk. The loads are
+            // row-strided DRAM accesses (~1 us each under load), so kExAhead of them are kept in flight and the
+            // first batch is issued BEFORE waiting for the accumulator.
+            constexpr int kExAhead = 4;
+            uint32_t ex[kExAhead][8];
             const bf16* exp_ = nullptr;
             if constexpr (!OUT_F32) {
                 if (p.addend != nullptr) exp_ = p.addend + static_cast<long long>(row) * p.ld_add;
                 else if (p.epilogue == VB_EPI_DGELU) exp_ = p.aux_in + static_cast<long long>(row) * p.ld_aux;
                 if (row >= p.M) exp_ = nullptr;
             }
+#pragma unroll
+            for (int k = 0; k < kExAhead; ++k)
+                if (exp_ != nullptr && col0 + k * 16 < p.N) ldg_v8(exp_ + col0 + k * 16, ex[k]);
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tcgen05_fence_after();
+            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + half * (BLOCK_N / 2);
+            uint32_t v[2][16];
             tmem_ld_32x32b_x16(taddr0, v[0]);
-            if (exp_ != nullptr && col0 < p.N) ldg_v8(exp_ + col0, ex[0]);
 #pragma unroll
             for (int k = 0; k < NCH; ++k) {
                 tmem_ld_wait();
-                if (k + 1 < NCH) {
-                    tmem_ld_32x32b_x16(taddr0 + (k + 1) * 16, v[(k + 1) & 1]);
-                    if (exp_ != nullptr && col0 + (k + 1) * 16 < p.N) ldg_v8(exp_ + col0 + (k + 1) * 16, ex[(k + 1) & 1]);
-                }
+                if (k + 1 < NCH) tmem_ld_32x32b_x16(taddr0 + (k + 1) * 16, v[(k + 1) & 1]);
+                if (k + kExAhead < NCH && exp_ != nullptr && col0 + (k + kExAhead) * 16 < p.N)
+                    ldg_v8(exp_ + col0 + (k + kExAhead) * 16, ex[(k + kExAhead) % kExAhead]);
                 const int col = col0 + k * 16;
                 if (row < p.M && col < p.N) {
                     float x[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[k & 1][i]);
-                    epilogue16<OUT_F32>(p, row, col, has_bias ? sb + half * (BLOCK_N / 2) + k * 16 : nullptr, ex[k & 1], x);
+                    epilogue16<OUT_F32>(p, row, col, has_bias ? sb + half * (BLOCK_N / 2) + k * 16 : nullptr, ex[k % kExAhead], x);
                 }
             }
             tcgen05_fence_before();
