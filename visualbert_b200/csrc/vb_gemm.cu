@@ -384,8 +384,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int k = 0; k < NCH; ++k) {
                 tmem_ld_wait();
                 if (k + 1 < NCH) tmem_ld_32x32b_x16(taddr0 + (k + 1) * 16, v[(k + 1) & 1]);
-                if (k + kExAhead < NCH && exp_ != nullptr && col0 + (k + kExAhead) * 16 < p.N)
-                    ldg_v8(exp_ + col0 + (k + kExAhead) * 16, ex[(k + kExAhead) % kExAhead]);
                 const int col = col0 + k * 16;
                 if (row < p.M && col < p.N) {
                     float x[16];
@@ -393,6 +391,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[k & 1][i]);
                     epilogue16<OUT_F32>(p, row, col, has_bias ? sb + half * (BLOCK_N / 2) + k * 16 : nullptr, ex[k % kExAhead], x);
                 }
+                // buffer k % kExAhead is free again: refill it with the operand of chunk k + kExAhead
+                if (k + kExAhead < NCH && exp_ != nullptr && col0 + (k + kExAhead) * 16 < p.N)
+                    ldg_v8(exp_ + col0 + (k + kExAhead) * 16, ex[k % kExAhead]);
             }
             tcgen05_fence_before();
             mbar_arrive(tempty_bar(acc));
@@ -602,8 +603,6 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             for (int k = 0; k < NCH; ++k) {
                 tmem_ld_wait();
                 if (k + 1 < NCH) tmem_ld_32x32b_x16(taddr0 + (k + 1) * 16, v[(k + 1) & 1]);
-                if (k + kExAhead < NCH && exp_ != nullptr && col0 + (k + kExAhead) * 16 < p.N)
-                    ldg_v8(exp_ + col0 + (k + kExAhead) * 16, ex[(k + kExAhead) % kExAhead]);
                 const int col = col0 + k * 16;
                 if (row < p.M && col < p.N) {
                     float x[16];
@@ -611,6 +610,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[k & 1][i]);
                     epilogue16<OUT_F32>(p, row, col, has_bias ? sb + half * (BLOCK_N / 2) + k * 16 : nullptr, ex[k % kExAhead], x);
                 }
+                // buffer k % kExAhead is free again: refill it with the operand of chunk k + kExAhead
+                if (k + kExAhead < NCH && exp_ != nullptr && col0 + (k + kExAhead) * 16 < p.N)
+                    ldg_v8(exp_ + col0 + (k + kExAhead) * 16, ex[k % kExAhead]);
             }
             tcgen05_fence_before();
             if (leader) mbar_arrive(tempty_bar(acc));
