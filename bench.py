@@ -265,6 +265,11 @@ def run_ours(args):
     F = hot_path_flops_per_pair(c)
     step_tf = (value / world) * F / 1e12
     kern_ms = {k: round(v["ms"] / args.steps, 3) for k, v in prof.items()}
+    traffic, traffic_src = None, None
+    tj = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01final_traffic.json")
+    if os.path.exists(tj) and args.config == "cfg2" and B == 256:  # the ncu capture is of this workload only
+        tr = json.load(open(tj))
+        traffic, traffic_src = tr["gemm_dram_bytes_per_launch_avg"], f"profiles/r01final_traffic.json ({tr['source']})"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -276,9 +281,12 @@ def run_ours(args):
                    "l2": "per-step working set (>12 GB of activations) is >> the 126 MB L2; no explicit flush needed"},
         "clocks": clk.summary(),
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all 12 GEMMs/layer, fwd+dgrad+wgrad)",
+        "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_2cta_kernel (all 12 GEMMs/layer fwd+dgrad+wgrad, projection, MLM decoder)",
                      "achieved": gemm_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": gemm_tf / peaks["bf16_sustained"], "traffic": None,
+                     "frac": gemm_tf / peaks["bf16_sustained"], "traffic": traffic,
+                     "traffic_note": ("DRAM read+write bytes per GEMM launch (ncu --set full, mean over one layer's 12 GEMM launches), "
+                                      + traffic_src) if traffic else "no ncu capture for this workload",
+                     "flops_per_launch": g["work"] / max(1, g["launches"]),
                      "of": peaks["source"] + " bf16_tflops_sustained", "launches_per_step": g["launches"] / args.steps,
                      "kernel_ms_per_step": round(g["ms"] / args.steps, 3)},
         "step_roofline": {"flops_per_pair": F, "achieved": step_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
