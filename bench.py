@@ -232,26 +232,47 @@ def run_ours(args):
         for _ in range(max(args.warmup, 3)):
             step(resident)
         barrier()
-        # ---- timed region: inputs resident in HBM ----
-        _lib.profile_read()
-        _lib.profile_enable(True)
+        # ---- timed region: inputs resident in HBM (no per-launch events: they cost ~2 % of the step) ----
         n0 = _lib.launch_count()
         clk.mark()
         ms_total = timed(lambda: step(resident), args.steps)
-    launches = _lib.launch_count() - n0
-    prof = _lib.profile_read()
-    _lib.profile_enable(False)
+        launches = _lib.launch_count() - n0
+        # ---- roofline pass: the SAME K steps again with a CUDA-event pair around every launch of the library ----
+        _lib.profile_read()
+        _lib.profile_enable(True)
+        ms_profiled = timed(lambda: step(resident), args.steps) / args.steps
+        prof = _lib.profile_read()
+        _lib.profile_enable(False)
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
 
     # ---- end to end: host (pinned) inputs, H2D + loss D2H inside the timed region ----
-    def e2e_step():
-        b = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()}
-        return float(step(b).item())
+    # every step copies ITS inputs from pinned host memory (BatchPrefetcher: on a copy stream, overlapping the previous
+    # step) and reads the loss back; K copies and K loss reads happen inside the timed region.
+    from visualbert_b200.parallel import BatchPrefetcher
+    pf = BatchPrefetcher(dev)
 
-    for _ in range(2):
-        e2e_step()
-    ms_e2e = timed(e2e_step, args.steps) / args.steps
+    def e2e_loop(steps):
+        staged = pf.stage(host)                      # step 0's inputs: not overlapped with anything
+        for i in range(steps):
+            batch = pf.take(staged)
+            if i + 1 < steps:
+                staged = pf.stage(host)              # step i+1's inputs, in flight while step i computes
+            float(step(batch).item())
+
+    e2e_loop(2)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    e2e_loop(args.steps)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    ms_e2e /= args.steps
     e2e_value = world * B / (ms_e2e * 1e-3)
 
     if rank != 0:
@@ -288,7 +309,9 @@ def run_ours(args):
                                       + traffic_src) if traffic else "no ncu capture for this workload",
                      "flops_per_launch": g["work"] / max(1, g["launches"]),
                      "of": peaks["source"] + " bf16_tflops_sustained", "launches_per_step": g["launches"] / args.steps,
-                     "kernel_ms_per_step": round(g["ms"] / args.steps, 3)},
+                     "kernel_ms_per_step": round(g["ms"] / args.steps, 3),
+                     "measured": f"per-launch CUDA events over a second pass of the same {args.steps} steps "
+                                 f"({ms_profiled:.2f} ms/step with the events enabled)"},
         "step_roofline": {"flops_per_pair": F, "achieved": step_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                           "frac": step_tf / peaks["bf16_sustained"],
                           "note": "hot-path algorithmic FLOPs (SURVEY.md §8d, heads and recompute not credited) over the whole step"},

@@ -29,7 +29,7 @@ def _gemm(_lib, L, st, **kw):
     _lib.check(L.vb_gemm(ctypes.byref(a), st), "vb_gemm")
 
 
-@pytest.mark.parametrize("M,N,K", [(256, 512, 128), (300, 784, 200), (384, 384, 768), (41984 // 8, 2304, 768)])
+@pytest.mark.parametrize("M,N,K", [(256, 512, 128), (300, 784, 200), (384, 384, 768), (512, 2112, 192), (41984 // 8, 2304, 768)])
 def test_gemm_tn(M, N, K):
     _lib, L, dev, st = _setup()
     torch.manual_seed(0)

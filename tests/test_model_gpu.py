@@ -213,3 +213,18 @@ def test_large_config_shapes_match_oracle():
         a, b = dict(model.named_parameters())[k].grad.float().reshape(-1), sdo[k].grad.reshape(-1)
         cos = torch.dot(a, b).item() / (a.norm().item() * b.norm().item())
         assert cos >= GRAD_COS, f"{k}: cosine {cos:.5f}"
+
+
+def test_batch_prefetcher_matches_direct_copy():
+    """parallel.BatchPrefetcher: staged copies on the side stream deliver the same tensors, in order."""
+    from visualbert_b200.parallel import BatchPrefetcher
+    dev = torch.device("cuda:0")
+    pf = BatchPrefetcher(dev)
+    hosts = [{"a": torch.randn(257, 33).pin_memory(), "b": torch.arange(i, i + 1000).pin_memory(), "tag": i} for i in range(4)]
+    staged = pf.stage(hosts[0])
+    for i in range(4):
+        batch = pf.take(staged)
+        if i + 1 < 4:
+            staged = pf.stage(hosts[i + 1])
+        assert batch["tag"] == i
+        assert torch.equal(batch["a"].cpu(), hosts[i]["a"]) and torch.equal(batch["b"].cpu(), hosts[i]["b"])

@@ -766,8 +766,9 @@ int gemm(const vb_gemm_args& a, cudaStream_t st) {
         p.drop_stream = a.dropout_stream;
     }
 
-    // BLOCK_N: 256 unless N is small or the 256-wide tiling wastes > 25 % of the last tile
-    const bool bn256 = (a.N >= 256) && ((a.N % 256 == 0) || (a.N % 256 > 192));
+    // BLOCK_N: 256 unless N is small or padding N up to a multiple of 256 wastes more than 1/8 of the columns
+    const int n_pad256 = (a.N + 255) / 256 * 256;
+    const bool bn256 = (a.N >= 256) && ((n_pad256 - a.N) * 8 <= a.N);
     const int BN = bn256 ? 256 : 128;
 
     CUtensorMap ta, tb;

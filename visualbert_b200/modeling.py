@@ -550,11 +550,18 @@ class TrainVisualBERTObjective(PreTrainedBertModel):
             self.flickr_attention = FlickrAttention(config)
         self.apply(self.init_bert_weights)
 
-    def _masked_lm_loss(self, sequence_output, flat_labels):
+    @staticmethod
+    def _labelled_rows(flat_labels):
+        """Indices of the rows that carry an MLM target. `nonzero` synchronises with the device, so forward() calls this
+        BEFORE the encoder is enqueued (the stream is empty then) instead of draining ~12 ms of queued work later."""
+        return torch.nonzero(flat_labels.contiguous().view(-1) != -1).squeeze(1)
+
+    def _masked_lm_loss(self, sequence_output, flat_labels, rows=None):
         """CrossEntropyLoss(ignore_index=-1) of the MLM head (M.py:1471-1473) evaluated on the labelled rows only:
         ignored rows contribute neither to the sum nor to the count, so value and gradients are unchanged."""
         labels = flat_labels.contiguous().view(-1)
-        rows = torch.nonzero(labels != -1).squeeze(1)
+        if rows is None:
+            rows = self._labelled_rows(flat_labels)
         hidden = sequence_output.reshape(-1, sequence_output.size(-1)).index_select(0, rows)
         head = self.cls.predictions
         if rows.numel() == 0 or not hidden.is_cuda:
@@ -598,6 +605,9 @@ class TrainVisualBERTObjective(PreTrainedBertModel):
         else:
             flat_attention_mask = flat_input_mask
 
+        mlm_rows = None
+        if self.training_head_type == "pretraining" and flat_masked_lm_labels is not None and not output_all_encoded_layers:
+            mlm_rows = self._labelled_rows(flat_masked_lm_labels)  # the only host sync of the step: do it up front
         sequence_output, pooled_output = self.bert(
             flat_input_ids, flat_token_type_ids, flat_attention_mask, visual_embeddings=flat_visual_embeddings,
             position_embeddings_visual=flat_position_embeddings_visual, visual_embeddings_type=visual_embeddings_type,
@@ -619,7 +629,7 @@ class TrainVisualBERTObjective(PreTrainedBertModel):
             output_dict["seq_relationship_score"] = seq_relationship_score
             output_dict["loss"] = None
             if flat_masked_lm_labels is not None:
-                masked_lm_loss = self._masked_lm_loss(sequence_output, flat_masked_lm_labels)
+                masked_lm_loss = self._masked_lm_loss(sequence_output, flat_masked_lm_labels, mlm_rows)
                 output_dict["masked_lm_loss"] = masked_lm_loss
                 output_dict["loss"] = masked_lm_loss
                 if is_random_next is not None:

@@ -71,3 +71,39 @@ def shard_batch(batch, rank, world_size):
         else:
             out[k] = v
     return out
+
+
+class BatchPrefetcher:
+    """Host→device staging of input batches on a copy stream, so the copy of batch i+1 overlaps the step on batch i.
+
+    Replaces the `.cuda()` the reference's training loop does on the batch before every forward
+    (`visualbert/models/model_wrapper.py:64-70`; DataParallel's scatter from host, `train.py:146`). Host tensors should
+    be pinned. Usage:
+
+        pf = BatchPrefetcher(device)
+        staged = pf.stage(next(it))
+        for ...:
+            batch = pf.take(staged)            # compute stream waits for the copy, not the host
+            staged = pf.stage(next(it))        # enqueue the next copy before launching this step
+            loss = step(batch)
+    """
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+
+    def stage(self, host_batch):
+        with torch.cuda.stream(self.stream):
+            dev = {k: (v.to(self.device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host_batch.items()}
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return dev, ev
+
+    def take(self, staged):
+        dev, ev = staged
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        for v in dev.values():
+            if torch.is_tensor(v):
+                v.record_stream(cur)  # allocated on the copy stream, consumed on the compute stream
+        return dev
