@@ -205,6 +205,32 @@ typedef struct {
 int vb_embed_fwd(const vb_embed_desc* d, void* y, const vb_embed_acts* acts, void* stream);
 int vb_embed_bwd(const vb_embed_desc* d, const vb_embed_acts* acts, const void* dy, const vb_embed_grads* g, void* stream);
 
+/* ---- BertAdam ------------------------------------------------------------------------
+ * Replaces the per-tensor Python loop of BertAdam.step, visualbert/pytorch_pretrained_bert/optimization.py:239-304:
+ * Adam WITHOUT bias correction (opt.py:299-302), decoupled weight decay added to the update (opt.py:287-288),
+ * gradient clipping PER PARAMETER TENSOR to max_grad_norm (opt.py:272-273, torch clip_grad_norm_ semantics:
+ * coef = max_norm / (||g||_2 + 1e-6), applied when < 1), learning rate already multiplied by the schedule value of
+ * the tensor's own step counter (opt.py:290-291) by the caller. One call = one optimizer step over all tensors of a
+ * table that lives in DEVICE memory; two launches (per-tensor sum of squares, update). Gradients are read, never
+ * modified (the reference scales p.grad in place as a side effect of the clip; callers zero it afterwards). */
+#define VB_ADAM_CHUNK 32768 /* elements per CTA; tensor i owns chunks [first_chunk, first_chunk + ceil(numel/CHUNK)) */
+typedef struct {
+    void* p;          /* fp32 parameter, updated in place */
+    const void* g;    /* fp32 gradient */
+    void* m;          /* fp32 next_m (state['next_m'], opt.py:262) */
+    void* v;          /* fp32 next_v (state['next_v'], opt.py:264) */
+    int64_t numel;
+    float lr;           /* group lr * schedule.get_lr(state['step']) */
+    float weight_decay; /* group weight_decay (0 for the bias / LayerNorm group, model_wrapper.py:106-111) */
+    int32_t first_chunk;
+    int32_t reserved;
+} vb_adam_tensor;     /* 56 bytes */
+/* table: device array [n_tensors] ordered by first_chunk; sumsq: device scratch [n_tensors] (overwritten).
+ * b1/b2/eps/max_grad_norm are doubles because the reference forms (1 - b) in double precision; max_grad_norm <= 0
+ * disables clipping (opt.py:272). */
+int vb_bert_adam_step(const vb_adam_tensor* table, int32_t n_tensors, int32_t n_chunks, float* sumsq, double b1, double b2,
+                      double eps, double max_grad_norm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

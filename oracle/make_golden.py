@@ -68,6 +68,9 @@ def main():
     M = import_reference()
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    make_bert_adam_golden(out_dir)
+    if "--only-adam" in sys.argv:
+        return
     for name in CASES:
         cfg, sd, batch, c = build_case(name)
         model = M.TrainVisualBERTObjective(M.BertConfig.from_dict(cfg), c["head"], visual_embedding_dim=c["Dv"])
@@ -107,6 +110,31 @@ def main():
             rec["grad_sub::" + k] = subsample(dict(model.named_parameters())[k].grad)
         np.savez_compressed(os.path.join(out_dir, name + ".npz"), **rec)
         print(f"{name}: loss={loss.item():.6f} logits{tuple(logits.shape)} -> {name}.npz")
+
+
+def make_bert_adam_golden(out_dir):
+    """Reference BertAdam (opt.py:185-304), 4 steps on seeded tensors: two parameter groups (decay / no decay) like
+    model_wrapper.py:106-111, warmup_linear schedule; gradients large enough that the per-parameter clip engages on
+    some tensors and not on others. Stores parameters and both moments after every step."""
+    from pytorch_pretrained_bert.optimization import BertAdam
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import adam_util
+    init, grads = adam_util.scenario()
+    shapes = adam_util.SHAPES
+    params = [torch.nn.Parameter(t.clone()) for t in init]
+    opt = BertAdam([{"params": params[:3], "weight_decay": 0.01}, {"params": params[3:], "weight_decay": 0.0}],
+                   **adam_util.HYPER)
+    rec = {"shapes": np.array([len(s) for s in shapes])}
+    for step in range(4):
+        for i, p in enumerate(params):
+            p.grad = grads[step][i].clone()
+        opt.step()
+        for i, p in enumerate(params):
+            rec[f"p{i}_s{step}"] = p.detach().numpy().copy()
+            rec[f"m{i}_s{step}"] = opt.state[p]["next_m"].numpy().copy()
+            rec[f"v{i}_s{step}"] = opt.state[p]["next_v"].numpy().copy()
+    np.savez_compressed(os.path.join(out_dir, "bert_adam.npz"), **rec)
+    print("bert_adam: 4 steps x", len(params), "tensors")
 
 
 if __name__ == "__main__":

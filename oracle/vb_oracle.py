@@ -171,3 +171,49 @@ def objective(sd, cfg, head, input_ids, token_type_ids, input_mask, visual_embed
     else:
         raise ValueError(head)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# BertAdam — restatement of visualbert/pytorch_pretrained_bert/optimization.py ("opt.py")
+# ------------------------------------------------------------------------------------------------
+def lr_schedule(name, step, warmup, t_total, cycles=0.5):
+    """Learning-rate multiplier of the `_LRSchedule` family (opt.py:37-182): `None`/'none' (ConstantLR, opt.py:84-86),
+    'warmup_cosine' (opt.py:89-112), 'warmup_constant' (opt.py:154-162), 'warmup_linear' (opt.py:165-174)."""
+    if t_total < 0:                                   # opt.py:61-62
+        return 1.0
+    warmup = max(float(warmup), 0.0)                  # opt.py:50
+    progress = float(step) / float(t_total)           # opt.py:63
+    if name in (None, "none"):
+        return 1.0
+    if name == "warmup_constant":
+        return progress / warmup if progress < warmup else 1.0
+    if name == "warmup_linear":
+        return progress / warmup if progress < warmup else max((progress - 1.0) / (warmup - 1.0), 0.0)
+    if name == "warmup_cosine":
+        if progress < warmup:
+            return progress / warmup
+        progress = (progress - warmup) / (1 - warmup)
+        return 0.5 * (1.0 + math.cos(math.pi * cycles * 2 * progress))
+    raise ValueError(name)
+
+
+def bert_adam_step(p, grad, m, v, step, lr, schedule="warmup_linear", warmup=-1, t_total=-1, b1=0.9, b2=0.999, e=1e-6,
+                   weight_decay=0.01, max_grad_norm=1.0):
+    """One BertAdam update of ONE parameter tensor (opt.py:253-297); returns (p, m, v, step+1, clipped grad).
+    Adam without bias correction (opt.py:299-302), decoupled weight decay added to the update (opt.py:287-288),
+    per-parameter gradient clipping (opt.py:272-273 -> torch clip_grad_norm_: coef = max_norm/(||g||+1e-6), applied
+    when < 1), schedule evaluated at the parameter's own step counter (opt.py:290-291)."""
+    g = grad.clone()
+    if max_grad_norm > 0:
+        norm = g.double().pow(2).sum().sqrt().to(g.dtype)
+        coef = max_grad_norm / (norm + 1e-6)
+        if coef < 1:
+            g = g * coef
+    m = m * b1 + (1 - b1) * g                          # opt.py:277
+    v = v * b2 + (1 - b2) * g * g                      # opt.py:278
+    update = m / (v.sqrt() + e)                        # opt.py:279
+    if weight_decay > 0.0:
+        update = update + weight_decay * p             # opt.py:287-288
+    lr_scheduled = lr * lr_schedule(schedule, step, warmup, t_total)   # opt.py:290-291
+    p = p - lr_scheduled * update                      # opt.py:293-294
+    return p, m, v, step + 1, g

@@ -26,15 +26,15 @@ def test_library_loads_and_exports_every_declared_symbol():
 def test_struct_mirrors_match_c_sizes(tmp_path):
     from visualbert_b200 import _lib
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "vbert_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include "vbert_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %d\\n",'
                    'sizeof(vb_gemm_args),sizeof(vb_layer_desc),sizeof(vb_layer_acts),sizeof(vb_layer_grads),'
-                   'sizeof(vb_layer_scratch),sizeof(vb_embed_desc),sizeof(vb_embed_acts),sizeof(vb_embed_grads));return 0;}\n')
+                   'sizeof(vb_layer_scratch),sizeof(vb_embed_desc),sizeof(vb_embed_acts),sizeof(vb_embed_grads),sizeof(vb_adam_tensor),VB_ADAM_CHUNK);return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     mirrors = [_lib.GemmArgs, _lib.LayerDesc, _lib.LayerActs, _lib.LayerGrads, _lib.LayerScratch, _lib.EmbedDesc,
-               _lib.EmbedActs, _lib.EmbedGrads]
-    assert sizes == [ctypes.sizeof(m) for m in mirrors]
+               _lib.EmbedActs, _lib.EmbedGrads, _lib.AdamTensor]
+    assert sizes == [ctypes.sizeof(m) for m in mirrors] + [_lib.VB_ADAM_CHUNK]
 
 
 def test_argument_validation_reports_through_vb_last_error():

@@ -28,11 +28,13 @@ def _worker(rank, world, port, q):
     b = shard_batch({"x": x, "y": y, "tag": "keep"}, rank, world)
     assert b["tag"] == "keep" and b["x"].shape[0] == 6
     torch.nn.functional.mse_loss(model(b["x"]), b["y"]).backward()
-    flat = sync.allreduce().clone()
+    sync.allreduce()
+    flat = torch.cat([v.reshape(-1) for v in sync.views]).clone()  # the views, without the alignment padding
     dist.all_reduce = orig
     assert len(calls) == 1, "exactly one collective per step"
     for p in model.parameters():
         assert p.grad.data_ptr() >= sync.flat.data_ptr()  # grads live inside the flat buffer
+        assert p.grad.data_ptr() % 256 == sync.flat.data_ptr() % 256  # every view starts on a 256-byte boundary
     if rank == 0:
         ref = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 3))
         ref.load_state_dict(model.state_dict())
@@ -69,3 +71,22 @@ def test_flat_grad_sync_single_process_and_tied_weights():
     s.zero()
     assert s.flat.abs().sum() == 0 and emb.weight.grad is s.views[0]
     s.allreduce()  # no process group: no-op
+
+
+def test_flat_grad_layout_keeps_qkv_adjacent_and_everything_else_aligned():
+    sys.path.insert(0, ROOT)
+    from visualbert_b200 import BertConfig, TrainVisualBERTObjective, synthetic
+    from visualbert_b200.parallel import FlatGradSync
+    cfg = BertConfig.from_dict(synthetic.bert_config_dict(2, 128, 2, 512, vocab=515))  # odd vocab: misaligning sizes
+    model = TrainVisualBERTObjective(cfg, "vqa", visual_embedding_dim=64)               # classifier bias 3129 (odd)
+    s = FlatGradSync(model)
+    base = s.flat.data_ptr()
+    for layer in model.bert.encoder.layer:
+        a = layer.attention.self
+        q, k, v = a.query.weight.grad, a.key.weight.grad, a.value.weight.grad
+        assert k.data_ptr() == q.data_ptr() + q.numel() * 4 and v.data_ptr() == k.data_ptr() + k.numel() * 4
+        bq, bk, bv = a.query.bias.grad, a.key.bias.grad, a.value.bias.grad
+        assert bk.data_ptr() == bq.data_ptr() + bq.numel() * 4 and bv.data_ptr() == bk.data_ptr() + bk.numel() * 4
+    for p in model.parameters():
+        if p.requires_grad:
+            assert (p.grad.data_ptr() - base) % 16 == 0, "16-byte vector access must stay legal"

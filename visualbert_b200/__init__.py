@@ -5,3 +5,4 @@ from .modeling import (BertConfig, BertLayerNorm, BertVisualModel, BertEmbedding
                        TrainVisualBERTObjective)
 
 __version__ = "0.1.0"
+from .optimization import BertAdam, WarmupLinearSchedule  # noqa: F401,E402

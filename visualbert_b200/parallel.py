@@ -31,14 +31,24 @@ class FlatGradSync:
         if not self.params:
             raise ValueError("FlatGradSync: module has no trainable parameters")
         dev = self.params[0].device
-        total = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
-        self.group = process_group
-        off = 0
-        self.views = []
+        # tensors inside an adjacency group stay back to back (the fused [3H, H] gradient needs that); every other
+        # tensor starts on a 256-byte boundary so 16-byte vector accesses (red.add.v4, the optimizer) stay legal
+        # whatever the sizes before it (decoder bias 30522, classifier bias 3129, ...)
+        packed = set()
+        for m in module.modules():
+            for group in getattr(m, "_vb_adjacent_param_groups", lambda: ())():
+                packed.update(id(p) for p in group[1:])
+        offsets, off = [], 0
         for p in self.params:
-            v = self.flat[off: off + p.numel()].view_as(p)
+            if id(p) not in packed:
+                off = (off + 63) // 64 * 64
+            offsets.append(off)
             off += p.numel()
+        self.flat = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.group = process_group
+        self.views = []
+        for p, o in zip(self.params, offsets):
+            v = self.flat[o: o + p.numel()].view_as(p)
             p.grad = v
             self.views.append(v)
 
