@@ -185,6 +185,9 @@ typedef struct {
     const float* b_proj;           /* [hidden] */
     const float* word; const float* pos; const float* type; const float* pos_vis; const float* type_vis; /* fp32 tables */
     const float* gamma; const float* beta;
+    const void* visual_addend;     /* bf16 [batch*num_regions, hidden] or NULL: extra additive term on the visual rows —
+                                      the VCR aligned position embeddings of M.py:1223-1245 (mean of the text position
+                                      embeddings a region is aligned to). Its gradient is vb_embed_grads.d_vis. */
 } vb_embed_desc;
 
 typedef struct {

@@ -33,6 +33,13 @@ CASES = {
                        batch=dict(B=4, T=10, V=8, ragged=True, nlvr_types=True)),
     "small_multichoice": dict(model=dict(layers=1, hidden=128, heads=2, inter=512, vocab=512), Dv=64,
                               head="multichoice", batch=dict(B=2, T=9, V=5, ragged=True, choices=4)),
+    # SURVEY.md §8f rank 4, the VCR-only branches of the reference
+    "small_vcr_alignment": dict(model=dict(layers=2, hidden=128, heads=2, inter=512, vocab=512), Dv=64, head="multichoice",
+                                batch=dict(B=2, T=9, V=5, ragged=True, choices=4, alignment=3)),
+    "small_bypass_nlvr": dict(model=dict(layers=2, hidden=128, heads=2, inter=512, vocab=512), Dv=64, head="nlvr",
+                              batch=dict(B=4, T=10, V=8, ragged=True, nlvr_types=True), flags=dict(bypass_transformer=True)),
+    "small_attention_weights": dict(model=dict(layers=2, hidden=128, heads=2, inter=512, vocab=512), Dv=64, head="nlvr",
+                                    batch=dict(B=3, T=10, V=6, ragged=True), flags=dict(output_attention_weights=True)),
     "base3_ragged_pretraining": dict(model=dict(layers=3, hidden=768, heads=12, inter=3072, vocab=2048), Dv=2048,
                                      head="pretraining", batch=dict(B=5, T=33, V=19, ragged=True)),
 }
@@ -52,7 +59,8 @@ def build_case(name):
     c = CASES[name]
     m = c["model"]
     cfg = synthetic.bert_config_dict(m["layers"], m["hidden"], m["heads"], m["inter"], vocab=m["vocab"])
-    sd = synthetic.init_state_dict(cfg, c["head"], c["Dv"], seed=0)
+    sd = synthetic.init_state_dict(cfg, c["head"], c["Dv"], seed=0,
+                                   bypass_transformer=c.get("flags", {}).get("bypass_transformer", False))
     b = dict(c["batch"])
     batch = synthetic.make_batch(Dv=c["Dv"], head=c["head"], seed=1234, vocab=m["vocab"], **b)
     return cfg, sd, batch, c
@@ -71,14 +79,26 @@ def main():
     make_bert_adam_golden(out_dir)
     if "--only-adam" in sys.argv:
         return
+    only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--case=")]
     for name in CASES:
+        if only and name not in only:
+            continue
         cfg, sd, batch, c = build_case(name)
-        model = M.TrainVisualBERTObjective(M.BertConfig.from_dict(cfg), c["head"], visual_embedding_dim=c["Dv"])
+        model = M.TrainVisualBERTObjective(M.BertConfig.from_dict(cfg), c["head"], visual_embedding_dim=c["Dv"],
+                                           **c.get("flags", {}))
         missing = model.load_state_dict(sd, strict=False)
         assert set(missing.missing_keys) <= {"cls.predictions.decoder.weight"}, missing
         assert not missing.unexpected_keys, missing
         model.eval()
         out = model(**batch)
+        if c.get("flags", {}).get("output_attention_weights"):
+            # analysis mode: the reference returns ONLY {"attention_weights": [L x [B, A, S, S]], "loss": None} (M.py:1430-1444)
+            assert out["loss"] is None and set(out) == {"attention_weights", "loss"}
+            rec = {f"attn{i}_sub": subsample(w) for i, w in enumerate(out["attention_weights"])}
+            rec["attn_shape"] = np.array(out["attention_weights"][0].shape)
+            np.savez_compressed(os.path.join(out_dir, name + ".npz"), **rec)
+            print(f"{name}: {len(out['attention_weights'])} attention maps {tuple(out['attention_weights'][0].shape)} -> {name}.npz")
+            continue
         loss = out["loss"]
         loss.backward()
         rec = {"loss": np.float64(loss.item())}
@@ -91,12 +111,22 @@ def main():
                                         logits.double().abs().max().item()])
         if "seq_relationship_score" in out:
             rec["nsp"] = out["seq_relationship_score"].detach().double().numpy()
-        # hidden states (second forward with output_all_encoded_layers)
-        with torch.no_grad():
-            enc = model(**{**batch, "output_all_encoded_layers": True})
-        for i, h in enumerate(enc["sequence_output"]):
-            rec[f"hidden{i}_sub"] = subsample(h)
-        rec["pooled"] = enc["pooled_output"].double().numpy()
+        if c.get("flags", {}).get("bypass_transformer"):
+            # the bypass model refuses output_all_encoded_layers (M.py:1300): capture the final hidden state with a hook
+            keep = {}
+            hook = model.bert.additional_layer.register_forward_hook(lambda m, i, o: keep.__setitem__("y", o))
+            with torch.no_grad():
+                model(**batch)
+            hook.remove()
+            rec[f"hidden{cfg['num_hidden_layers'] - 1}_sub"] = subsample(keep["y"])
+            rec["pooled"] = model.bert.pooler(keep["y"]).detach().double().numpy()
+        else:
+            # hidden states (second forward with output_all_encoded_layers)
+            with torch.no_grad():
+                enc = model(**{**batch, "output_all_encoded_layers": True})
+            for i, h in enumerate(enc["sequence_output"]):
+                rec[f"hidden{i}_sub"] = subsample(h)
+            rec["pooled"] = enc["pooled_output"].double().numpy()
         names, norms = [], []
         for k, p in model.named_parameters():
             if p.grad is not None:

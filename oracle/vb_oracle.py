@@ -82,29 +82,46 @@ def self_attention(sd, pfx, x, ext_mask, num_heads, return_probs=False):
     return (ctx, probs) if return_probs else ctx
 
 
-def bert_layer(sd, pfx, x, ext_mask, num_heads):
-    """M.py:331-341 with 270-274, 302-305, 315-319."""
-    ctx = self_attention(sd, pfx + "attention.self.", x, ext_mask, num_heads)
+def bert_layer(sd, pfx, x, ext_mask, num_heads, return_probs=False):
+    """M.py:331-341 with 270-274, 302-305, 315-319; return_probs = the output_attention_weights branch (M.py:332-336)."""
+    ctx = self_attention(sd, pfx + "attention.self.", x, ext_mask, num_heads, return_probs)
+    if return_probs:
+        ctx, probs = ctx
     a = layer_norm(linear(ctx, sd, pfx + "attention.output.dense") + x,
                    sd[pfx + "attention.output.LayerNorm.weight"], sd[pfx + "attention.output.LayerNorm.bias"])
     h = gelu(linear(a, sd, pfx + "intermediate.dense"))
-    return layer_norm(linear(h, sd, pfx + "output.dense") + a,
-                      sd[pfx + "output.LayerNorm.weight"], sd[pfx + "output.LayerNorm.bias"])
+    y = layer_norm(linear(h, sd, pfx + "output.dense") + a,
+                   sd[pfx + "output.LayerNorm.weight"], sd[pfx + "output.LayerNorm.bias"])
+    return (y, probs) if return_probs else y
 
 
 def visual_model(sd, cfg, input_ids, token_type_ids, attention_mask, visual_embeddings,
-                 visual_embeddings_type, image_text_alignment=None, pfx="bert."):
-    """BertVisualModel.forward, M.py:1275-1333 (default branch). Returns (all layers, pooled)."""
+                 visual_embeddings_type, image_text_alignment=None, pfx="bert.", bypass_transformer=False,
+                 output_attention_weights=False):
+    """BertVisualModel.forward, M.py:1275-1333. Returns (all layers, pooled[, attention probabilities per layer]).
+    bypass_transformer (M.py:1299-1314): the encoder sees the TEXT positions only (mask sliced to the text keys), the
+    visual rows of the embedding output are appended afterwards and one extra BertLayer runs over the full sequence."""
     dt = sd[pfx + "embeddings.word_embeddings.weight"].dtype
     ext = (1.0 - attention_mask[:, None, None, :].to(dt)) * -10000.0
     x = embeddings(sd, input_ids, token_type_ids, visual_embeddings, visual_embeddings_type,
                    image_text_alignment, pfx + "embeddings.")
-    layers = []
+    A = cfg["num_attention_heads"]
+    if bypass_transformer and visual_embeddings is not None:
+        T = input_ids.size(1)
+        t, vis = x[:, :T], x[:, T:]
+        for i in range(cfg["num_hidden_layers"]):
+            t = bert_layer(sd, f"{pfx}encoder.layer.{i}.", t, ext[..., :T], A)
+        y = bert_layer(sd, pfx + "additional_layer.", torch.cat((t, vis), dim=1), ext, A)
+        return [y], torch.tanh(linear(y[:, 0], sd, pfx + "pooler.dense"))
+    layers, probs = [], []
     for i in range(cfg["num_hidden_layers"]):
-        x = bert_layer(sd, f"{pfx}encoder.layer.{i}.", x, ext, cfg["num_attention_heads"])
+        x = bert_layer(sd, f"{pfx}encoder.layer.{i}.", x, ext, A, output_attention_weights)
+        if output_attention_weights:
+            x, pr = x
+            probs.append(pr)
         layers.append(x)
     pooled = torch.tanh(linear(x[:, 0], sd, pfx + "pooler.dense"))  # M.py:380-386
-    return layers, pooled
+    return (layers, pooled, probs) if output_attention_weights else (layers, pooled)
 
 
 def _flat2(t):
@@ -125,7 +142,7 @@ def pretraining_heads(sd, seq, pooled):
 
 def objective(sd, cfg, head, input_ids, token_type_ids, input_mask, visual_embeddings, image_mask,
               visual_embeddings_type=None, label=None, masked_lm_labels=None, is_random_next=None,
-              image_text_alignment=None):
+              image_text_alignment=None, bypass_transformer=False, output_attention_weights=False):
     """TrainVisualBERTObjective.forward, M.py:1373-1598 for heads pretraining / vqa / nlvr /
     multichoice, eval mode (dropout off). Returns the reference's output dict."""
     ids, tt, im = _flat2(input_ids), _flat2(token_type_ids), _flat2(input_mask)
@@ -137,9 +154,13 @@ def objective(sd, cfg, head, input_ids, token_type_ids, input_mask, visual_embed
         full = torch.full_like(am, -1)
         full[:, : lab.size(1)] = lab
         lab = full
-    layers, pooled = visual_model(sd, cfg, ids, tt, am, ve, vt, ali)
+    res = visual_model(sd, cfg, ids, tt, am, ve, vt, ali, bypass_transformer=bypass_transformer,
+                       output_attention_weights=output_attention_weights)
+    layers, pooled = res[0], res[1]
     seq = layers[-1]
     out = {"sequence_output": seq, "pooled_output": pooled}
+    if output_attention_weights:  # analysis mode: nothing but the attention maps is returned (M.py:1430-1444)
+        return {"attention_weights": res[2], "loss": None}
     if head == "pretraining":
         logits, nsp = pretraining_heads(sd, seq, pooled)
         out["logits"], out["seq_relationship_score"], out["loss"] = logits, nsp, None

@@ -22,7 +22,8 @@ def load(name):
     c = cases()[name]
     m = c["model"]
     cfg = synthetic.bert_config_dict(m["layers"], m["hidden"], m["heads"], m["inter"], vocab=m["vocab"])
-    sd = synthetic.init_state_dict(cfg, c["head"], c["Dv"], seed=0)
+    sd = synthetic.init_state_dict(cfg, c["head"], c["Dv"], seed=0,
+                                   bypass_transformer=c.get("flags", {}).get("bypass_transformer", False))
     batch = synthetic.make_batch(Dv=c["Dv"], head=c["head"], seed=1234, vocab=m["vocab"], **c["batch"])
     gold = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False))
     return cfg, sd, batch, c, gold

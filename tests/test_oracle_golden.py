@@ -9,7 +9,7 @@ import golden_util
 import vb_oracle
 
 CASE_NAMES = ["cfg1_pretraining", "small_ragged_pretraining", "small_vqa", "small_nlvr", "small_multichoice",
-              "base3_ragged_pretraining"]
+              "base3_ragged_pretraining", "small_vcr_alignment", "small_bypass_nlvr"]
 
 
 def _close(a, b, rtol, what):
@@ -24,7 +24,7 @@ def test_oracle_matches_reference_outputs(name):
     cfg, sd, batch, c, gold = golden_util.load(name)
     sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     kw = {k: v for k, v in batch.items() if k != "position_embeddings_visual"}
-    out = vb_oracle.objective(sd, cfg, c["head"], **kw)
+    out = vb_oracle.objective(sd, cfg, c["head"], **kw, **c.get("flags", {}))
     _close(out["loss"].item(), gold["loss"], 2e-5, "loss")
     for k in ("masked_lm_loss", "next_sentence_loss"):
         if k in gold:
@@ -45,6 +45,18 @@ def test_oracle_matches_reference_outputs(name):
         assert abs(mine.double().norm().item() - g) <= 5e-5 * max(g, 1e-6) + 1e-9, f"grad norm {k}"
     for key in [k for k in gold if k.startswith("grad_sub::")]:
         _close(golden_util.subsample(sd[key.split("::", 1)[1]].grad), gold[key], 5e-5, key)
+
+
+def test_oracle_attention_weights_mode_matches_reference():
+    """output_attention_weights=True (M.py:1430-1444): only the per-layer attention maps are returned."""
+    cfg, sd, batch, c, gold = golden_util.load("small_attention_weights")
+    kw = {k: v for k, v in batch.items() if k != "position_embeddings_visual"}
+    out = vb_oracle.objective(sd, cfg, c["head"], **kw, **c["flags"])
+    assert out["loss"] is None and set(out) == {"attention_weights", "loss"}
+    assert len(out["attention_weights"]) == cfg["num_hidden_layers"]
+    assert list(out["attention_weights"][0].shape) == gold["attn_shape"].tolist()
+    for i, w in enumerate(out["attention_weights"]):
+        _close(golden_util.subsample(w), gold[f"attn{i}_sub"], 2e-5, f"attention map {i}")
 
 
 def test_fp64_oracle_agrees_with_fp32_reference():

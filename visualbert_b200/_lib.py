@@ -54,7 +54,8 @@ EmbedDesc = _struct("EmbedDesc", [
     ("eps", c_f32), ("dropout", c_f32), ("seed", c_u64),
     ("input_ids", _P), ("token_type_ids", _P), ("visual_type", _P), ("visual_feats", _P),
     ("w_proj", _P), ("b_proj", _P),
-    ("word", _P), ("pos", _P), ("type", _P), ("pos_vis", _P), ("type_vis", _P), ("gamma", _P), ("beta", _P)])
+    ("word", _P), ("pos", _P), ("type", _P), ("pos_vis", _P), ("type_vis", _P), ("gamma", _P), ("beta", _P),
+    ("visual_addend", _P)])
 EmbedActs = _struct("EmbedActs", [(n, _P) for n in ("vis_proj", "pre", "mean", "rstd")])
 EmbedGrads = _struct("EmbedGrads", [(n, _P) for n in (
     "dword", "dpos", "dtype", "dpos_vis", "dtype_vis", "dw_proj", "db_proj", "dgamma", "dbeta",

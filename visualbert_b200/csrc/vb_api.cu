@@ -143,6 +143,10 @@ int embed_fwd_api(const vb_embed_desc* d, void* y, const vb_embed_acts* s, cudaS
     if (BV > 0) {
         vb_gemm_args a = fwd_args(d->visual_feats, d->w_proj, s->vis_proj, BV, d->hidden, d->visual_dim);
         a.bias = d->b_proj;
+        if (d->visual_addend != nullptr) {  // aligned position embeddings ride the projection GEMM's residual input
+            a.addend = d->visual_addend;
+            a.ld_add = d->hidden;
+        }
         VB_TRY(gemm(a, st));
     }
     EmbedParams p;

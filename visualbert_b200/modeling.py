@@ -183,21 +183,42 @@ class BertLayer(nn.Module):
                     seed=int(seed), cache=self._weights)
         return ops.bert_layer(hidden_states.to(torch.bfloat16), attention_mask.float().contiguous(), meta, self._params())
 
+    @torch.no_grad()
+    def attention_probabilities(self, hidden_states, attention_mask):
+        """softmax(QK^T/sqrt(d) + mask) [B, A, S, S] in fp32 — the tensor `output_attention_weights=True` asks for
+        (M.py:241-247, 258-259). The fused kernels never materialise it, so this analysis-only slow path recomputes it
+        with torch ops from the layer input; pre-dropout, detached."""
+        if attention_mask.dim() == 4:
+            attention_mask = attention_mask[:, 0, 0, :]
+        a = self.attention.self
+        x = hidden_states.float()
+        B, S, H = x.shape
+        A = a.num_attention_heads
+
+        def heads(lin):
+            return F.linear(x, lin.weight.float(), lin.bias.float()).view(B, S, A, H // A).permute(0, 2, 1, 3)
+
+        scores = torch.matmul(heads(a.query), heads(a.key).transpose(-1, -2)) / math.sqrt(H // A)
+        return torch.softmax(scores + attention_mask.float()[:, None, None, :], dim=-1)
+
 
 class BertEncoder(nn.Module):
     def __init__(self, config):
         super().__init__()
         self.layer = nn.ModuleList([BertLayer(config, i) for i in range(config.num_hidden_layers)])
+        self.output_attention_weights = getattr(config, "output_attention_weights", False)
 
     def forward(self, hidden_states, attention_mask, output_all_encoded_layers=True, seed=0):
-        outs = []
+        outs, attn = [], []
         for layer in self.layer:
+            if self.output_attention_weights:
+                attn.append(layer.attention_probabilities(hidden_states, attention_mask))
             hidden_states = layer(hidden_states, attention_mask, seed)
             if output_all_encoded_layers:
                 outs.append(hidden_states)
         if not output_all_encoded_layers:
             outs.append(hidden_states)
-        return outs
+        return (outs, attn) if self.output_attention_weights else outs
 
 
 class BertPooler(nn.Module):
@@ -235,10 +256,20 @@ class BertEmbeddingsWithVisualEmbedding(nn.Module):
 
     def forward(self, input_ids, token_type_ids=None, visual_embeddings=None, visual_embeddings_type=None,
                 position_embeddings_visual=None, image_text_alignment=None, confidence=None, seed=0):
-        if image_text_alignment is not None:
-            raise NotImplementedError(
-                "visualbert_b200: the VCR image_text_alignment branch (M.py:1223-1245) is not implemented in the "
-                "CUDA embedding kernel (SURVEY.md §8f rank 4)")
+        vis_extra = None
+        if image_text_alignment is not None and visual_embeddings is not None:
+            # VCR branch (M.py:1223-1245): every region also gets the MEAN of the text position embeddings of the words
+            # it is aligned to (-1 = padding; regions without any aligned word get 0). A gather over [B, V, A] indices —
+            # done with torch ops (autograd reaches position_embeddings.weight) and handed to the CUDA path as an
+            # additive term on the projected region rows.
+            ali_mask = (image_text_alignment != -1)
+            table = self.position_embeddings.weight
+            gathered = table[(image_text_alignment * ali_mask.long())] * ali_mask.unsqueeze(-1).to(table.dtype)
+            count = ali_mask.sum(2).clamp_(min=1).to(table.dtype)
+            vis_extra = gathered.sum(2) / count.unsqueeze(-1)
+            if vis_extra.size(1) != visual_embeddings.size(1):  # alignment padded longer than the regions (M.py:1241-1243)
+                assert vis_extra.size(1) >= visual_embeddings.size(1)
+                vis_extra = vis_extra[:, : visual_embeddings.size(1), :]
         if token_type_ids is None:
             token_type_ids = torch.zeros_like(input_ids)
         if visual_embeddings is not None and visual_embeddings_type is None:
@@ -248,7 +279,7 @@ class BertEmbeddingsWithVisualEmbedding(nn.Module):
             meta, input_ids, token_type_ids, visual_embeddings_type, visual_embeddings,
             self.word_embeddings.weight, self.position_embeddings.weight, self.token_type_embeddings.weight,
             self.token_type_embeddings_visual.weight, self.position_embeddings_visual.weight,
-            self.projection.weight, self.projection.bias, self.LayerNorm.weight, self.LayerNorm.bias)
+            self.projection.weight, self.projection.bias, self.LayerNorm.weight, self.LayerNorm.bias, vis_extra)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -389,17 +420,13 @@ class BertVisualModel(PreTrainedBertModel):
 
     def __init__(self, config):
         super().__init__(config)
-        if getattr(config, "bypass_transformer", False):
-            raise NotImplementedError("visualbert_b200: bypass_transformer=True (M.py:1299-1314) is not implemented")
-        if getattr(config, "output_attention_weights", False):
-            raise NotImplementedError(
-                "visualbert_b200: output_attention_weights=True (M.py:1316-1324) is not available — the fused attention "
-                "kernel never materialises the probability tensor")
         self.embeddings = BertEmbeddingsWithVisualEmbedding(config)
         self.encoder = BertEncoder(config)
         self.pooler = BertPooler(config)
-        self.bypass_transformer = False
-        self.output_attention_weights = False
+        self.bypass_transformer = getattr(config, "bypass_transformer", False)
+        if self.bypass_transformer:  # M.py:1268-1269; its own dropout streams (layer index after the encoder's)
+            self.additional_layer = BertLayer(config, config.num_hidden_layers)
+        self.output_attention_weights = getattr(config, "output_attention_weights", False)
         self.apply(self.init_bert_weights)
         self._step = 0
         self.dropout_seed = 0x5EED
@@ -422,11 +449,25 @@ class BertVisualModel(PreTrainedBertModel):
         x = self.embeddings(input_ids, token_type_ids, visual_embeddings=visual_embeddings,
                             visual_embeddings_type=visual_embeddings_type, position_embeddings_visual=position_embeddings_visual,
                             image_text_alignment=image_text_alignment, confidence=confidence, seed=seed)
-        encoded_layers = self.encoder(x, bias, output_all_encoded_layers=output_all_encoded_layers, seed=seed)
+        if self.bypass_transformer and visual_embeddings is not None:
+            # M.py:1299-1314: the encoder runs over the text positions only (keys masked to the text part), the region
+            # rows of the embedding output are appended afterwards and one more BertLayer sees the whole sequence
+            assert not output_all_encoded_layers  # "Don't support this for the bypass model" (M.py:1300)
+            T = input_ids.size(1)
+            text = self.encoder(x[:, :T].contiguous(), bias[:, :T].contiguous(), output_all_encoded_layers=False, seed=seed)
+            text = text[0][-1] if self.output_attention_weights else text[-1]
+            final = self.additional_layer(torch.cat((text, x[:, T:]), dim=1), bias, seed)
+            return final, self.pooler(final)
+        if self.output_attention_weights:
+            encoded_layers, attn = self.encoder(x, bias, output_all_encoded_layers=output_all_encoded_layers, seed=seed)
+        else:
+            encoded_layers = self.encoder(x, bias, output_all_encoded_layers=output_all_encoded_layers, seed=seed)
         sequence_output = encoded_layers[-1]
         pooled_output = self.pooler(sequence_output)
         if not output_all_encoded_layers:
             encoded_layers = encoded_layers[-1]
+        if self.output_attention_weights:
+            return encoded_layers, pooled_output, attn
         return encoded_layers, pooled_output
 
 
@@ -608,6 +649,14 @@ class TrainVisualBERTObjective(PreTrainedBertModel):
         mlm_rows = None
         if self.training_head_type == "pretraining" and flat_masked_lm_labels is not None and not output_all_encoded_layers:
             mlm_rows = self._labelled_rows(flat_masked_lm_labels)  # the only host sync of the step: do it up front
+        if self.output_attention_weights:
+            # analysis mode (M.py:1430-1444): nothing but the per-layer attention maps is returned
+            attention_weights = self.bert(
+                flat_input_ids, flat_token_type_ids, flat_attention_mask, visual_embeddings=flat_visual_embeddings,
+                position_embeddings_visual=flat_position_embeddings_visual, visual_embeddings_type=visual_embeddings_type,
+                image_text_alignment=flat_image_text_alignment, confidence=flat_confidence,
+                output_all_encoded_layers=output_all_encoded_layers)[2]
+            return {"attention_weights": attention_weights, "loss": None}
         sequence_output, pooled_output = self.bert(
             flat_input_ids, flat_token_type_ids, flat_attention_mask, visual_embeddings=flat_visual_embeddings,
             position_embeddings_visual=flat_position_embeddings_visual, visual_embeddings_type=visual_embeddings_type,

@@ -239,7 +239,8 @@ class _EmbedFn(torch.autograd.Function):
     """BertEmbeddingsWithVisualEmbedding.forward (reference M.py:1198-1257) through vb_embed_fwd / vb_embed_bwd."""
 
     @staticmethod
-    def forward(ctx, meta, input_ids, token_type_ids, visual_type, feats, word, pos, typ, typ_vis, pos_vis, pw, pb, gamma, beta):
+    def forward(ctx, meta, input_ids, token_type_ids, visual_type, feats, word, pos, typ, typ_vis, pos_vis, pw, pb, gamma, beta,
+                vis_extra=None):
         _require_cuda(word, "bert_embeddings")
         dev = word.device
         B, T = input_ids.shape
@@ -255,8 +256,9 @@ class _EmbedFn(torch.autograd.Function):
             fb = cast_to_bf16(f) if f.dtype == torch.float32 else f.to(_BF16).contiguous()
             wp = meta["cache"].get(pw)
             vis_proj = torch.empty(B * V, H, device=dev, dtype=_BF16)
+            xb = None if vis_extra is None else vis_extra.detach().reshape(B * V, H).to(_BF16).contiguous()
         else:
-            Dv, vt, fb, wp, vis_proj = 0, None, None, None, None
+            Dv, vt, fb, wp, vis_proj, xb = 0, None, None, None, None, None
         pre = torch.empty(M, H, device=dev, dtype=_BF16)
         mean = torch.empty(M, device=dev, dtype=torch.float32)
         rstd = torch.empty(M, device=dev, dtype=torch.float32)
@@ -266,7 +268,8 @@ class _EmbedFn(torch.autograd.Function):
             n_types=typ.shape[0], eps=1e-12, dropout=meta["dropout"], seed=meta["seed"],
             input_ids=ids.data_ptr(), token_type_ids=tt.data_ptr(), visual_type=_ptr(vt), visual_feats=_ptr(fb),
             w_proj=_ptr(wp), b_proj=_ptr(pb), word=word.data_ptr(), pos=pos.data_ptr(), type=typ.data_ptr(),
-            pos_vis=pos_vis.data_ptr(), type_vis=typ_vis.data_ptr(), gamma=gamma.data_ptr(), beta=beta.data_ptr())
+            pos_vis=pos_vis.data_ptr(), type_vis=typ_vis.data_ptr(), gamma=gamma.data_ptr(), beta=beta.data_ptr(),
+            visual_addend=_ptr(xb))
         a = _lib.EmbedActs(vis_proj=_ptr(vis_proj), pre=pre.data_ptr(), mean=mean.data_ptr(), rstd=rstd.data_ptr())
         _lib.check(_lib.lib().vb_embed_fwd(ctypes.byref(d), ctypes.c_void_p(y.data_ptr()), ctypes.byref(a), _stream()),
                    "vb_embed_fwd")
@@ -275,6 +278,7 @@ class _EmbedFn(torch.autograd.Function):
         ctx.feats_need_grad = feats is not None and feats.requires_grad
         ctx.feats_dtype = None if feats is None else feats.dtype
         ctx.feats_shape = None if feats is None else feats.shape
+        ctx.extra = None if (vis_extra is None or not vis_extra.requires_grad) else (vis_extra.shape, vis_extra.dtype)
         ctx.params = (word, pos, typ, typ_vis, pos_vis, pw, pb, gamma, beta)
         ctx.save_for_backward(ids, tt, vt, fb, wp, pb, word, pos, typ, typ_vis, pos_vis, gamma, beta, pre, mean, rstd)
         return y
@@ -323,14 +327,18 @@ class _EmbedFn(torch.autograd.Function):
         dfe = None
         if d_feats is not None:
             dfe = d_feats.view(ctx.feats_shape).to(ctx.feats_dtype)
+        # the gradient of anything added to the projected region rows is d_vis itself
+        dex = None if ctx.extra is None else d_vis.view(ctx.extra[0]).to(ctx.extra[1])
         if direct is not None:
-            return (None, None, None, None, dfe) + (None,) * 9
-        return (None, None, None, None, dfe, dword, dpos, dtyp, dtyp_vis, dpos_vis, dpw, dpb, dgamma, dbeta)
+            return (None, None, None, None, dfe) + (None,) * 9 + (dex,)
+        return (None, None, None, None, dfe, dword, dpos, dtyp, dtyp_vis, dpos_vis, dpw, dpb, dgamma, dbeta, dex)
 
 
-def bert_embeddings(meta, input_ids, token_type_ids, visual_type, feats, word, pos, typ, typ_vis, pos_vis, pw, pb, gamma, beta):
+def bert_embeddings(meta, input_ids, token_type_ids, visual_type, feats, word, pos, typ, typ_vis, pos_vis, pw, pb, gamma, beta,
+                    vis_extra=None):
+    """vis_extra: optional [B, V, H] term added to the projected region rows before the LayerNorm (differentiable)."""
     return _EmbedFn.apply(meta, input_ids, token_type_ids, visual_type, feats, word, pos, typ, typ_vis, pos_vis, pw, pb,
-                          gamma, beta)
+                          gamma, beta, vis_extra)
 
 
 # --------------------------------------------------------------------------------------------

@@ -24,8 +24,25 @@ def bert_config_dict(layers, hidden, heads, inter, vocab=30522, max_pos=512, p_d
                 initializer_range=0.02)
 
 
-def param_shapes(cfg, head, visual_dim):
-    """Reference state_dict keys → shapes, in registration order."""
+def _layer_shapes(s, p, H, I):
+    for n in ("query", "key", "value"):
+        s[p + f"attention.self.{n}.weight"] = (H, H)
+        s[p + f"attention.self.{n}.bias"] = (H,)
+    s[p + "attention.output.dense.weight"] = (H, H)
+    s[p + "attention.output.dense.bias"] = (H,)
+    s[p + "attention.output.LayerNorm.weight"] = (H,)
+    s[p + "attention.output.LayerNorm.bias"] = (H,)
+    s[p + "intermediate.dense.weight"] = (I, H)
+    s[p + "intermediate.dense.bias"] = (I,)
+    s[p + "output.dense.weight"] = (H, I)
+    s[p + "output.dense.bias"] = (H,)
+    s[p + "output.LayerNorm.weight"] = (H,)
+    s[p + "output.LayerNorm.bias"] = (H,)
+
+
+def param_shapes(cfg, head, visual_dim, bypass_transformer=False):
+    """Reference state_dict keys → shapes. `bert.additional_layer.*` (bypass_transformer, M.py:1268-1269)
+    is appended LAST so that the seeded draws of all other keys do not depend on the flag."""
     H, I, Vc = cfg["hidden_size"], cfg["intermediate_size"], cfg["vocab_size"]
     P, Tv = cfg["max_position_embeddings"], cfg["type_vocab_size"]
     s = {}
@@ -40,20 +57,7 @@ def param_shapes(cfg, head, visual_dim):
     s[e + "projection.weight"] = (H, visual_dim)
     s[e + "projection.bias"] = (H,)
     for i in range(cfg["num_hidden_layers"]):
-        p = f"bert.encoder.layer.{i}."
-        for n in ("query", "key", "value"):
-            s[p + f"attention.self.{n}.weight"] = (H, H)
-            s[p + f"attention.self.{n}.bias"] = (H,)
-        s[p + "attention.output.dense.weight"] = (H, H)
-        s[p + "attention.output.dense.bias"] = (H,)
-        s[p + "attention.output.LayerNorm.weight"] = (H,)
-        s[p + "attention.output.LayerNorm.bias"] = (H,)
-        s[p + "intermediate.dense.weight"] = (I, H)
-        s[p + "intermediate.dense.bias"] = (I,)
-        s[p + "output.dense.weight"] = (H, I)
-        s[p + "output.dense.bias"] = (H,)
-        s[p + "output.LayerNorm.weight"] = (H,)
-        s[p + "output.LayerNorm.bias"] = (H,)
+        _layer_shapes(s, f"bert.encoder.layer.{i}.", H, I)
     s["bert.pooler.dense.weight"] = (H, H)
     s["bert.pooler.dense.bias"] = (H,)
     if head in ("pretraining", "vqa_advanced", "flickr"):
@@ -70,15 +74,17 @@ def param_shapes(cfg, head, visual_dim):
         s["classifier.weight"], s["classifier.bias"] = (3129, H), (3129,)
     elif head == "nlvr":
         s["classifier.weight"], s["classifier.bias"] = (2, H), (2,)
+    if bypass_transformer:
+        _layer_shapes(s, "bert.additional_layer.", H, I)
     return s
 
 
-def init_state_dict(cfg, head, visual_dim, seed=0, dtype=torch.float32):
+def init_state_dict(cfg, head, visual_dim, seed=0, dtype=torch.float32, bypass_transformer=False):
     """Seeded random init: matrices N(0, 0.02) (reference M.py:473-484); LayerNorm weights 1+N(0,0.1)
     and all biases N(0, 0.05) so that no parameter is trivially 0/1 in parity tests."""
     g = torch.Generator().manual_seed(seed)
     sd = {}
-    for k, shp in param_shapes(cfg, head, visual_dim).items():
+    for k, shp in param_shapes(cfg, head, visual_dim, bypass_transformer).items():
         if k.endswith("LayerNorm.weight"):
             t = 1.0 + 0.1 * torch.randn(shp, generator=g)
         elif k.endswith("bias"):
@@ -90,11 +96,13 @@ def init_state_dict(cfg, head, visual_dim, seed=0, dtype=torch.float32):
 
 
 def make_batch(B, T, V, Dv, head="pretraining", seed=1234, ragged=False, vocab=30522, nlvr_types=False,
-               choices=None):
+               choices=None, alignment=None):
     """Reference tensor-dict for TrainVisualBERTObjective.forward (M.py:1373-1392).
 
     ragged=True draws text lengths ~U[T/2, T] and region counts ~U[V/2, V] (parity tests);
-    choices=C produces VCR-style 3-D ids [B, C, T] / 4-D features [B, C, V, Dv]."""
+    choices=C produces VCR-style 3-D ids [B, C, T] / 4-D features [B, C, V, Dv];
+    alignment=A adds VCR `image_text_alignment` [.., V, A]: text positions each region is tied to, -1 = padding
+    (M.py:1223-1245), drawn AFTER everything else so the other tensors do not depend on it."""
     g = torch.Generator().manual_seed(seed)
     lead = (B,) if choices is None else (B, choices)
     n = B if choices is None else B * choices
@@ -133,4 +141,9 @@ def make_batch(B, T, V, Dv, head="pretraining", seed=1234, ragged=False, vocab=3
         batch["label"] = torch.randint(0, 2, (n,), generator=g)
     elif head == "multichoice":
         batch["label"] = torch.randint(0, choices or 4, (B,), generator=g)
+    if alignment:
+        ali = torch.randint(0, T, (n, V, alignment), generator=g)
+        ali = torch.where(torch.rand(n, V, alignment, generator=g) < 0.4, torch.full_like(ali, -1), ali)
+        ali[:, 0, :] = -1  # a region without any aligned word: the divide-by-zero guard of M.py:1236
+        batch["image_text_alignment"] = ali.view(*lead, V, alignment)
     return batch
