@@ -130,6 +130,8 @@ attn_fwd_head_kernel(const AttnParams p, const int nkb) {
 
     int item = blockIdx.x;
     if (item >= total) return;
+    pdl_trigger();
+    pdl_wait();
     issue(item, 0);
     int buf = 0;
     for (; item < total; item += gridDim.x, buf ^= 1) {
@@ -176,6 +178,8 @@ attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, floa
                   int A, int H) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;  // token index b*S + q
+    pdl_trigger();
+    pdl_wait();
     if (row >= static_cast<long long>(B) * S) return;
     const int b = static_cast<int>(row / S), q = static_cast<int>(row % S);
     const int chunks = H >> 3;  // 8 chunks of 8 elements per head
@@ -242,6 +246,8 @@ attn_bwd_head_kernel(const AttnParams p, const int nkb, const int nbuf) {
 
     int item = blockIdx.x;
     if (item >= total) return;
+    pdl_trigger();
+    pdl_wait();
     if (nbuf == 2) issue(item, 0);
     int buf = 0;
     for (; item < total; item += gridDim.x) {
@@ -407,7 +413,7 @@ static int launch_fwd(const AttnParams& p, int nkb, cudaStream_t st) {
     const int total = p.B * p.A;
     const int grid = total < num_sms() ? total : num_sms();
     ProfScope ps(st, PROF_ATTN_FWD, 4.0 * p.B * p.A * p.S * p.S * kHd, 1);
-    attn_fwd_head_kernel<NW><<<grid, NW * 32, smem, st>>>(p, nkb);
+    VB_CHECK_CUDA(launch_pdl(attn_fwd_head_kernel<NW>, dim3(grid), dim3(NW * 32), smem, st, p, nkb));
     return 0;
 }
 
@@ -436,7 +442,7 @@ static int launch_bwd(const AttnParams& p, int nkb, cudaStream_t st) {
     const int total = p.B * p.A;
     const int grid = total < num_sms() ? total : num_sms();
     ProfScope ps(st, PROF_ATTN_DKV, 7.0 * p.B * p.A * p.S * p.S * kHd, 1);
-    attn_bwd_head_kernel<NW><<<grid, NW * 32, smem, st>>>(p, nkb, nbuf);
+    VB_CHECK_CUDA(launch_pdl(attn_bwd_head_kernel<NW>, dim3(grid), dim3(NW * 32), smem, st, p, nkb, nbuf));
     return 0;
 }
 
@@ -444,7 +450,8 @@ int attn_bwd_head(const AttnParams& p, int nkb, cudaStream_t st) {
     {
         const long long rows = static_cast<long long>(p.B) * p.S;
         ProfScope ps(st, PROF_ATTN_DQ, 1.0 * p.B * p.A * p.S * p.S * kHd, 1);
-        attn_delta_kernel<<<static_cast<int>((rows + 7) / 8), 256, 0, st>>>(p.ctx, p.dctx, p.drow, p.B, p.S, p.A, p.H);
+        VB_CHECK_CUDA(launch_pdl(attn_delta_kernel, dim3(static_cast<int>((rows + 7) / 8)), dim3(256), 0, st, p.ctx, p.dctx, p.drow, p.B,
+                                 p.S, p.A, p.H));
     }
     const int nw = (p.S + 15) / 16;
     int rc;

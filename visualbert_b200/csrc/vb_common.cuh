@@ -24,6 +24,32 @@ int num_sms();
 // the launch stream and tags them with a category and the algorithmic work (FLOPs or bytes) of the call.
 enum { PROF_GEMM_FWD = 0, PROF_GEMM_DGRAD = 1, PROF_GEMM_WGRAD = 2, PROF_ATTN_FWD = 3, PROF_ATTN_DQ = 4, PROF_ATTN_DKV = 5,
        PROF_LN_FWD = 6, PROF_LN_BWD = 7, PROF_COLSUM = 8, PROF_EMBED = 9, PROF_OTHER = 10, PROF_NCAT = 11 };
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------
+// Hot-path kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel's CTAs may be
+// scheduled, and run their on-chip prologue (barrier init, TMEM allocation, tensor-map prefetch), while the previous
+// kernel's last CTAs drain. Every such kernel calls pdl_trigger() on entry and pdl_wait() BEFORE its first global
+// memory access (griddepcontrol.wait returns once the preceding grid has completed and its writes are visible).
+// VB_PDL=0 in the environment turns the attribute off (plain stream order).
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 struct ProfScope {
     ProfScope(cudaStream_t st, int cat, double work, int launches);
     ~ProfScope();

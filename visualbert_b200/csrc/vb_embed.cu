@@ -197,6 +197,8 @@ __global__ void __launch_bounds__(256)
 colsum_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ out, int M, int N) {
     __shared__ float red[8][32][9];
     const int ch = blockIdx.x * 32 + threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (ch * 8 < N) {
         const int stride = gridDim.y * 8;
@@ -314,7 +316,7 @@ int colsum(const void* x, long long ld, float* out, int M, int N, cudaStream_t s
     if (gy > (M + 7) / 8) gy = (M + 7) / 8;
     {
         ProfScope ps(st, PROF_COLSUM, 2.0 * M * N, 1);
-        colsum_kernel<<<dim3(gx, gy), dim3(32, 8), 0, st>>>(static_cast<const bf16*>(x), ld, out, M, N);
+        VB_CHECK_CUDA(launch_pdl(colsum_kernel, dim3(gx, gy), dim3(32, 8), 0, st, static_cast<const bf16*>(x), ld, out, M, N));
     }
     VB_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -260,6 +260,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_trigger();
+    pdl_wait();  // everything above is on-chip set-up; operands of the previous kernel are read only from here on
 
     const int m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
     const int n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
@@ -481,6 +483,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     cluster_sync_all();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_trigger();
+    pdl_wait();  // everything above is on-chip set-up; operands of the previous kernel are read only from here on
 
     const int m_blocks = (p.M + 255) / 256;
     const int n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
@@ -695,7 +699,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
     const int grid = tiles < num_sms() ? tiles : num_sms();
     {
         ProfScope ps(st, OUT_F32 ? PROF_GEMM_WGRAD : (B_MN ? PROF_GEMM_DGRAD : PROF_GEMM_FWD), 2.0 * p.M * p.N * p.K, 1);
-        kern<<<grid, kThreads, C::SMEM_BYTES, st>>>(ta, tb, p);
+        VB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), C::SMEM_BYTES, st, ta, tb, p));
     }
     VB_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -714,10 +718,18 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
     if (clusters > tiles) clusters = tiles;
     {
         ProfScope ps(st, OUT_F32 ? PROF_GEMM_WGRAD : (B_MN ? PROF_GEMM_DGRAD : PROF_GEMM_FWD), 2.0 * p.M * p.N * p.K, 1);
-        kern<<<2 * clusters, kThreads, Cfg2::SMEM_BYTES, st>>>(ta, tb, p);
+        VB_CHECK_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(kThreads), Cfg2::SMEM_BYTES, st, ta, tb, p));
     }
     VB_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("VB_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
 }
 
 // VB_GEMM_2CTA=0 disables the CTA-pair kernels (testing / tuning)

@@ -21,6 +21,8 @@ ln_fwd_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict
               float* __restrict__ rstd_out, int rows, int H, float eps) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * kLnWarps + warp;
+    pdl_trigger();
+    pdl_wait();
     if (row >= rows) return;
     const int chunks = H >> 3;
     float v[NC][8];
@@ -112,11 +114,13 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
     const int chunks = H >> 3;
     float4* sgam = sm4;
     float4* acc = sm4 + 2 * chunks + warp * 6 * chunks;
+    pdl_trigger();
+    for (int i = threadIdx.x; i < kLnWarps * 6 * chunks; i += blockDim.x) sm4[2 * chunks + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    pdl_wait();  // the accumulators are cleared while the previous kernel drains; global memory is touched from here on
     for (int i = threadIdx.x; i < 2 * chunks; i += blockDim.x) {
         const int h = i / chunks, ch = i % chunks;
         sgam[i] = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8 + h * 4));
     }
-    for (int i = threadIdx.x; i < kLnWarps * 6 * chunks; i += blockDim.x) sm4[2 * chunks + i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
 
     const float invH = 1.0f / H;
@@ -217,7 +221,8 @@ int ln_fwd(const void* x, long long ldx, const float* gamma, const float* beta, 
     const bf16* xb = static_cast<const bf16*>(x);
     bf16* yb = static_cast<bf16*>(y);
     ProfScope ps(st, PROF_LN_FWD, 4.0 * rows * H, 1);  // bytes: read + write bf16
-#define VB_LN_FWD(NC) ln_fwd_kernel<NC><<<grid, kLnWarps * 32, 0, st>>>(xb, ldx, gamma, beta, yb, ldy, mean, rstd, rows, H, eps)
+#define VB_LN_FWD(NC) \
+    VB_CHECK_CUDA(launch_pdl(ln_fwd_kernel<NC>, dim3(grid), dim3(kLnWarps * 32), 0, st, xb, ldx, gamma, beta, yb, ldy, mean, rstd, rows, H, eps))
     switch (nc) {
         case 1: VB_LN_FWD(1); break;
         case 2: VB_LN_FWD(2); break;
@@ -254,10 +259,10 @@ int ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, 
     }
     ProfScope ps(st, PROF_LN_BWD, (dx_drop ? 8.0 : 6.0) * rows * H, 1);
 #define VB_LN_BWD(NC)                                                                                        \
-    ln_bwd_kernel<NC><<<grid, kLnWarps * 32, smem, st>>>(                                                    \
+    VB_CHECK_CUDA(launch_pdl(ln_bwd_kernel<NC>, dim3(grid), dim3(kLnWarps * 32), smem, st,                  \
         static_cast<const bf16*>(dy), static_cast<const bf16*>(x), mean, rstd, gamma, static_cast<bf16*>(dx), \
         static_cast<bf16*>(dx_drop), dgamma, dbeta, dbias, rows, H, scale, th, seed, stream_id, in_scale,    \
-        in_th, in_stream_id)
+        in_th, in_stream_id))
     switch (nc) {
         case 1: VB_LN_BWD(1); break;
         case 2: VB_LN_BWD(2); break;
