@@ -402,6 +402,171 @@ attn_bwd_head_kernel(const AttnParams p, const int nkb, const int nbuf) {
 // ------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// backward, "PS" variant: P and dS of the whole head are kept in shared memory between the two phases, so the dK/dV
+// phase neither recomputes S^T = K Q^T and dP^T = V dO^T (64 of its 128 HMMAs per 16x64 unit) nor the exp2 / mask /
+// dropout work: it is two GEMMs whose A operands come from shared memory with ldmatrix.trans.
+//   phase A (rows = queries): S, P, dP, dS once; dQ += dS K;  P_drop and dS -> smem as bf16 [q][key] (pitch = 2*cols+16 B:
+//            an odd number of 16-byte chunks, so the 4-byte accumulator stores and the 8-row ldmatrix reads are
+//            bank-conflict free)
+//   phase B (rows = keys):    dV += P_drop^T dO,  dK += dS^T Q
+// Shared memory: Q|K|V|dO tiles (single buffer) + 2 x (lse, D, bias) vectors + P + dS = 227 KB at S = 164 (the limit), so
+// the next head cannot be double-buffered entirely: its K and V tiles (not needed by phase B) and its vectors are
+// prefetched during phase B, Q and dO at the top of its own iteration.
+// ------------------------------------------------------------------------------------------------
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+attn_bwd_head_ps_kernel(const AttnParams p, const int nkb, const int colsP) {
+    constexpr int NT = NW * 32;
+    extern __shared__ __align__(128) uint8_t dsmem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int S = p.S;
+    const long long ld = 3LL * p.H;
+    const int np64 = nkb * kBlk;
+    const int tile_bytes = 4 * nkb * kTileBytes;
+    const int pitch = colsP * 2 + 16;            // bytes per P / dS row
+    const int rowsP = colsP;                     // query rows kept (= ceil16(S))
+    float* svec_all = reinterpret_cast<float*>(dsmem + tile_bytes);              // [2][3][np64]
+    const uint32_t sbase = smem_u32(dsmem);
+    const uint32_t sQ = sbase, sK = sbase + nkb * kTileBytes, sV = sbase + 2 * nkb * kTileBytes, sdO = sbase + 3 * nkb * kTileBytes;
+    const uint32_t sP = sbase + tile_bytes + 2 * 3 * np64 * 4;
+    const uint32_t sDS = sP + rowsP * pitch;
+    const int total = p.B * p.A;
+    const float sc2 = p.scale * kLog2e;
+    const int row0 = warp * 16;
+    const bool active = row0 < S;
+    const bool drop = p.drop_scale != 0.f;
+    const float ds = drop ? p.drop_scale : 1.f;
+
+    auto issue_kv = [&](int item, int vb) {
+        const int b = item / p.A, h = item % p.A;
+        const bf16* qbase = p.qkv + static_cast<long long>(b) * S * ld + h * kHd;
+        load_rows<NT>(sK, qbase + p.H, ld, nkb, S, tid);
+        load_rows<NT>(sV, qbase + 2 * p.H, ld, nkb, S, tid);
+        cp_async_commit();
+        float* sv = svec_all + vb * 3 * np64;
+        const float* lsep = p.lse + static_cast<long long>(item) * S;
+        const float* drp = p.drow + static_cast<long long>(item) * S;
+        for (int i = tid; i < np64; i += NT) {
+            sv[i] = i < S ? lsep[i] * kLog2e : INFINITY;  // +inf => p = 0 for padded queries
+            sv[np64 + i] = i < S ? drp[i] : 0.f;
+            sv[2 * np64 + i] = i < S ? p.mask_bias[static_cast<long long>(b) * S + i] * kLog2e : -INFINITY;
+        }
+    };
+    auto issue_qdo = [&](int item) {
+        const int b = item / p.A, h = item % p.A;
+        load_rows<NT>(sQ, p.qkv + static_cast<long long>(b) * S * ld + h * kHd, ld, nkb, S, tid);
+        load_rows<NT>(sdO, p.dctx + static_cast<long long>(b) * S * p.H + h * kHd, p.H, nkb, S, tid);
+        cp_async_commit();
+    };
+
+    int item = blockIdx.x;
+    if (item >= total) return;
+    pdl_trigger();
+    pdl_wait();
+    issue_kv(item, 0);
+    int vb = 0;
+    for (; item < total; item += gridDim.x, vb ^= 1) {
+        issue_qdo(item);
+        cp_async_wait<0>();
+        __syncthreads();
+        const int b = item / p.A, h = item % p.A;
+        const unsigned bh = static_cast<unsigned>(item);
+        const float* slse = svec_all + vb * 3 * np64;
+        const float* sD = slse + np64;
+        const float* sbias = slse + 2 * np64;
+        bf16* dbase = p.dqkv + static_cast<long long>(b) * S * ld + h * kHd;
+        const int mytile = warp >> 2, myrow = (warp & 3) * 16;
+
+        // ---------------- phase A: S, P, dP, dS once; dQ; P_drop / dS -> shared memory ----------------
+        if (active) {
+            uint32_t qf[4][4], dof[4][4];
+            load_afrag(qf, sQ + mytile * kTileBytes, myrow, lane);
+            load_afrag(dof, sdO + mytile * kTileBytes, myrow, lane);
+            const float lse0 = slse[row0 + g], lse1 = slse[row0 + g + 8];
+            const float d0 = sD[row0 + g], d1 = sD[row0 + g + 8];
+            const uint32_t prow0 = (row0 + g) * pitch, prow1 = (row0 + g + 8) * pitch;
+            float dq[8][4];
+            zero_acc(dq);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int kvalid = min(kBlk, S - kb * kBlk);
+                unsigned long long keep_a = ~0ull, keep_c = ~0ull;
+                if (drop) {
+                    const unsigned long long* kp = p.keep + (static_cast<unsigned long long>(bh) * np64) * nkb;
+                    keep_a = kp[static_cast<long long>(row0 + g) * nkb + kb];
+                    keep_c = kp[static_cast<long long>(row0 + g + 8) * nkb + kb];
+                }
+                float s[8][4];
+                zero_acc(s);
+                gemm_nt(s, qf, sK + kb * kTileBytes, lane, kvalid);
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {  // dP = dO V^T in two 32-key halves (register pressure)
+                    float dp[4][4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+                    gemm_nt_half(dp, dof, sV + kb * kTileBytes, lane, hh, kvalid);
+#pragma unroll
+                    for (int n4 = 0; n4 < 4; ++n4) {
+                        const int nt = hh * 4 + n4, bit = nt * 8 + 2 * t;
+                        const float b0 = sbias[kb * kBlk + bit], b1 = sbias[kb * kBlk + bit + 1];
+                        const float p0 = fast_ex2(fmaf(s[nt][0], sc2, b0) - lse0), p1 = fast_ex2(fmaf(s[nt][1], sc2, b1) - lse0);
+                        const float p2 = fast_ex2(fmaf(s[nt][2], sc2, b0) - lse1), p3 = fast_ex2(fmaf(s[nt][3], sc2, b1) - lse1);
+                        const bool k0 = (keep_a >> bit) & 1ull, k1 = (keep_a >> (bit + 1)) & 1ull;
+                        const bool k2 = (keep_c >> bit) & 1ull, k3 = (keep_c >> (bit + 1)) & 1ull;
+                        const float e0 = k0 ? dp[n4][0] * ds : 0.f, e1 = k1 ? dp[n4][1] * ds : 0.f;
+                        const float e2 = k2 ? dp[n4][2] * ds : 0.f, e3 = k3 ? dp[n4][3] * ds : 0.f;
+                        s[nt][0] = p0 * (e0 - d0); s[nt][1] = p1 * (e1 - d0);
+                        s[nt][2] = p2 * (e2 - d1); s[nt][3] = p3 * (e3 - d1);
+                        const int col = kb * kBlk + bit;
+                        if (col < colsP) {  // warp-uniform per (kb, nt): colsP is a multiple of 16
+                            st_shared_u32(sP + prow0 + col * 2, pack_bf16x2(k0 ? p0 * ds : 0.f, k1 ? p1 * ds : 0.f));
+                            st_shared_u32(sP + prow1 + col * 2, pack_bf16x2(k2 ? p2 * ds : 0.f, k3 ? p3 * ds : 0.f));
+                            st_shared_u32(sDS + prow0 + col * 2, pack_bf16x2(s[nt][0], s[nt][1]));
+                            st_shared_u32(sDS + prow1 + col * 2, pack_bf16x2(s[nt][2], s[nt][3]));
+                        }
+                    }
+                }
+                uint32_t dsf[4][4];
+                acc_to_afrag(dsf, s);
+                gemm_nn(dq, dsf, sK + kb * kTileBytes, lane, kvalid);
+            }
+            store_acc(dbase, ld, row0, S, dq, lane, p.scale, p.scale);
+        }
+        __syncthreads();  // P / dS complete; K and V tiles are dead from here on
+
+        const int next = item + gridDim.x;
+        if (next < total) issue_kv(next, vb ^ 1);  // overlaps phase B
+
+        // ---------------- phase B: dV = P_drop^T dO, dK = dS^T Q for key rows row0 .. row0+15 ----------------
+        if (active) {
+            float dk[8][4], dv[8][4];
+            zero_acc(dk);
+            zero_acc(dv);
+            // ldmatrix.trans address of this lane: matrix i = lane >> 3 -> (query half i >> 1, key half i & 1)
+            const uint32_t a_off = (((lane >> 4) & 1) * 8 + (lane & 7)) * pitch + (row0 + ((lane >> 3) & 1) * 8) * 2;
+            for (int qb = 0; qb < nkb; ++qb) {
+                const int qvalid = min(kBlk, rowsP - qb * kBlk);
+                if (qvalid <= 0) break;
+                uint32_t af[4][4];
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    if (ks * 16 < qvalid)
+                        ldsm_x4_t(sP + (qb * kBlk + ks * 16) * pitch + a_off, af[ks][0], af[ks][1], af[ks][2], af[ks][3]);
+                gemm_nn(dv, af, sdO + qb * kTileBytes, lane, qvalid);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    if (ks * 16 < qvalid)
+                        ldsm_x4_t(sDS + (qb * kBlk + ks * 16) * pitch + a_off, af[ks][0], af[ks][1], af[ks][2], af[ks][3]);
+                gemm_nn(dk, af, sQ + qb * kTileBytes, lane, qvalid);
+            }
+            store_acc(dbase + p.H, ld, row0, S, dk, lane, p.scale, p.scale);
+            store_acc(dbase + 2 * p.H, ld, row0, S, dv, lane, 1.f, 1.f);
+        }
+        __syncthreads();  // Q / dO tiles and P / dS are free for the next head
+    }
+}
+
 template <int NW>
 static int launch_fwd(const AttnParams& p, int nkb, cudaStream_t st) {
     const int smem = 2 * 3 * nkb * kTileBytes + 2 * nkb * kBlk * 4;
@@ -446,6 +611,36 @@ static int launch_bwd(const AttnParams& p, int nkb, cudaStream_t st) {
     return 0;
 }
 
+// P/dS-in-shared-memory variant: only when the whole head fits (S <= ~176); VB_ATTN_BWD_PS=0 disables it
+template <int NW>
+static int launch_bwd_ps(const AttnParams& p, int nkb, int colsP, int smem, cudaStream_t st) {
+    static int configured = 0;
+    if (configured < smem) {
+        VB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_head_ps_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = smem;
+    }
+    const int total = p.B * p.A;
+    const int grid = total < num_sms() ? total : num_sms();
+    ProfScope ps(st, PROF_ATTN_DKV, 5.0 * p.B * p.A * p.S * p.S * kHd, 1);
+    VB_CHECK_CUDA(launch_pdl(attn_bwd_head_ps_kernel<NW>, dim3(grid), dim3(NW * 32), smem, st, p, nkb, colsP));
+    return 0;
+}
+
+static int bwd_ps_smem(const AttnParams& p, int nkb, int* colsP) {
+    static int enabled = -1, max_smem = 0;
+    if (enabled < 0) {
+        const char* e = getenv("VB_ATTN_BWD_PS");
+        enabled = (e && e[0] == '0') ? 0 : 1;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    }
+    if (!enabled) return 0;
+    *colsP = (p.S + 15) / 16 * 16;
+    const int smem = 4 * nkb * kTileBytes + 2 * 3 * nkb * kBlk * 4 + 2 * (*colsP) * ((*colsP) * 2 + 16);
+    return smem <= max_smem ? smem : 0;
+}
+
 int attn_bwd_head(const AttnParams& p, int nkb, cudaStream_t st) {
     {
         const long long rows = static_cast<long long>(p.B) * p.S;
@@ -454,8 +649,14 @@ int attn_bwd_head(const AttnParams& p, int nkb, cudaStream_t st) {
                                  p.S, p.A, p.H));
     }
     const int nw = (p.S + 15) / 16;
-    int rc;
-    if (nw <= 4) rc = launch_bwd<4>(p, nkb, st);
+    int rc, colsP = 0;
+    const int ps_smem = bwd_ps_smem(p, nkb, &colsP);
+    if (ps_smem > 0) {
+        if (nw <= 4) rc = launch_bwd_ps<4>(p, nkb, colsP, ps_smem, st);
+        else if (nw <= 8) rc = launch_bwd_ps<8>(p, nkb, colsP, ps_smem, st);
+        else if (nw <= 12) rc = launch_bwd_ps<12>(p, nkb, colsP, ps_smem, st);
+        else rc = launch_bwd_ps<16>(p, nkb, colsP, ps_smem, st);
+    } else if (nw <= 4) rc = launch_bwd<4>(p, nkb, st);
     else if (nw <= 8) rc = launch_bwd<8>(p, nkb, st);
     else if (nw <= 12) rc = launch_bwd<12>(p, nkb, st);
     else rc = launch_bwd<16>(p, nkb, st);
