@@ -28,11 +28,54 @@ __device__ __forceinline__ void load_rows(uint32_t tiles, const bf16* base, long
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// attention-probability dropout mask for the whole-head forward kernel: one thread per 64-bit word (query row, 64-key
+// block), 16 counter hashes -> 64 keep decisions of 8 random bits each (keep iff byte >= thresh8). Drawing the bits
+// inside the attention kernel cost 65 us per layer at the benchmark shape (it is latency/issue bound and the hashing
+// was ~40 % of its instructions); this kernel has nothing else to do and runs at full issue rate (~20 us).
+// The position of a decision inside the word is arbitrary (all are i.i.d.), so the four decisions of a hash are taken
+// SWAR-style: adding (256 - thresh8) to each byte carries into bit 8 of its 16-bit lane exactly when byte >= thresh8.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+attn_keep_mask_kernel(unsigned long long* __restrict__ keep, long long nwords, int nkb, int np64, int S, unsigned seed,
+                      unsigned thresh8) {
+    pdl_trigger();
+    pdl_wait();
+    const long long w = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+    if (w >= nwords) return;
+    const int row = static_cast<int>((w / nkb) % np64);
+    if (row >= S) { keep[w] = ~0ull; return; }
+    const uint32_t add = (256u - thresh8) * 0x00010001u;
+    const uint32_t base = static_cast<uint32_t>(w) * 16u;
+    uint32_t word[2];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t h = mix32((base + half * 8 + j) ^ seed);
+            const uint32_t de = ((h & 0x00ff00ffu) + add) & 0x01000100u;         // bytes 0, 2 -> bits 8, 24
+            const uint32_t dd = (((h >> 8) & 0x00ff00ffu) + add) & 0x01000100u;  // bytes 1, 3 -> bits 8, 24
+            acc |= (de >> (8 - j)) | (dd << j);  // bits {j, 16+j} and {8+j, 24+j}: every bit of the word used once
+        }
+        word[half] = acc;
+    }
+    keep[w] = static_cast<unsigned long long>(word[0]) | (static_cast<unsigned long long>(word[1]) << 32);
+}
+
 // one 64-key block of the forward pass for a 16-row warp tile (same math as the staged kernel)
 __device__ __forceinline__ void fwd_block(const AttnParams& p, float (&o)[8][4], float (&m)[2], float (&l)[2],
                                           const uint32_t (&qf)[4][4], uint32_t sK, uint32_t sV, const float* sbias,
                                           int kb, int kvalid, int qrow0, unsigned bh, int nkb, int lane, float sc2) {
     const int g = lane >> 2, t = lane & 3;
+    // keep bits of the two query rows of this lane for this key block (written by attn_keep_mask_kernel): issued before
+    // the QK^T MMAs so the loads are back long before the bits are needed
+    unsigned long long keep_a = ~0ull, keep_c = ~0ull;
+    if (p.drop_scale != 0.f) {
+        const unsigned long long* kp = p.keep + (static_cast<unsigned long long>(bh) * (nkb * kBlk)) * nkb;
+        keep_a = kp[static_cast<long long>(qrow0 + g) * nkb + kb];
+        keep_c = kp[static_cast<long long>(qrow0 + g + 8) * nkb + kb];
+    }
     float s[8][4];
     zero_acc(s);
     gemm_nt(s, qf, sK, lane, kvalid);
@@ -74,21 +117,13 @@ __device__ __forceinline__ void fwd_block(const AttnParams& p, float (&o)[8][4],
         o[nt][2] *= alpha[1]; o[nt][3] *= alpha[1];
     }
     if (p.drop_scale != 0.f) {
-        const int qa = qrow0 + g, qc = qa + 8;
-        const uint32_t ka_bits = attn_keep16(p.drop_seed, bh, qa, kb, t, p.S, p.drop_thresh16);
-        const uint32_t kc_bits = attn_keep16(p.drop_seed, bh, qc, kb, t, p.S, p.drop_thresh16);
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
-            s[nt][0] = ((ka_bits >> (2 * nt)) & 1u) ? s[nt][0] * p.drop_scale : 0.f;
-            s[nt][1] = ((ka_bits >> (2 * nt + 1)) & 1u) ? s[nt][1] * p.drop_scale : 0.f;
-            s[nt][2] = ((kc_bits >> (2 * nt)) & 1u) ? s[nt][2] * p.drop_scale : 0.f;
-            s[nt][3] = ((kc_bits >> (2 * nt + 1)) & 1u) ? s[nt][3] * p.drop_scale : 0.f;
-        }
-        const unsigned long long ma = quad_mask64(ka_bits, t), mc = quad_mask64(kc_bits, t);
-        if (t == 0) {
-            unsigned long long* kp = p.keep + (static_cast<unsigned long long>(bh) * (nkb * kBlk)) * nkb;
-            kp[static_cast<long long>(qa) * nkb + kb] = ma;
-            kp[static_cast<long long>(qc) * nkb + kb] = mc;
+            const int bit = nt * 8 + 2 * t;
+            s[nt][0] = ((keep_a >> bit) & 1ull) ? s[nt][0] * p.drop_scale : 0.f;
+            s[nt][1] = ((keep_a >> (bit + 1)) & 1ull) ? s[nt][1] * p.drop_scale : 0.f;
+            s[nt][2] = ((keep_c >> bit) & 1ull) ? s[nt][2] * p.drop_scale : 0.f;
+            s[nt][3] = ((keep_c >> (bit + 1)) & 1ull) ? s[nt][3] * p.drop_scale : 0.f;
         }
     }
     uint32_t pf[4][4];
@@ -585,6 +620,14 @@ static int launch_fwd(const AttnParams& p, int nkb, cudaStream_t st) {
 int attn_fwd_head(const AttnParams& p, int nkb, cudaStream_t st) {
     const int nw = (p.S + 15) / 16;
     int rc;
+    if (p.drop_scale != 0.f) {
+        const int np64 = nkb * kBlk;
+        const long long nwords = static_cast<long long>(p.B) * p.A * np64 * nkb;
+        VB_REQUIRE(nwords * 16 < (1LL << 32), "attention dropout: mask counter space exceeded (B*A*S too large)");
+        ProfScope ps(st, PROF_ATTN_FWD, 0.0, 1);
+        VB_CHECK_CUDA(launch_pdl(attn_keep_mask_kernel, dim3(static_cast<unsigned>((nwords + 255) / 256)), dim3(256), 0, st, p.keep,
+                                 nwords, nkb, np64, p.S, p.drop_seed, p.drop_thresh16));
+    }
     if (nw <= 4) rc = launch_fwd<4>(p, nkb, st);
     else if (nw <= 8) rc = launch_fwd<8>(p, nkb, st);
     else if (nw <= 12) rc = launch_fwd<12>(p, nkb, st);
