@@ -30,11 +30,9 @@ __device__ __forceinline__ void load_rows(uint32_t tiles, const bf16* base, long
 
 // ------------------------------------------------------------------------------------------------
 // attention-probability dropout mask for the whole-head forward kernel: one thread per 64-bit word (query row, 64-key
-// block), 16 counter hashes -> 64 keep decisions of 8 random bits each (keep iff byte >= thresh8). Drawing the bits
+// block), 16 counter hashes -> 64 keep decisions of 8 random bits each (keep iff value >= thresh8). Drawing the bits
 // inside the attention kernel cost 65 us per layer at the benchmark shape (it is latency/issue bound and the hashing
 // was ~40 % of its instructions); this kernel has nothing else to do and runs at full issue rate (~20 us).
-// The position of a decision inside the word is arbitrary (all are i.i.d.), so the four decisions of a hash are taken
-// SWAR-style: adding (256 - thresh8) to each byte carries into bit 8 of its 16-bit lane exactly when byte >= thresh8.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 attn_keep_mask_kernel(unsigned long long* __restrict__ keep, long long nwords, int nkb, int np64, int S, unsigned seed,
@@ -45,20 +43,21 @@ attn_keep_mask_kernel(unsigned long long* __restrict__ keep, long long nwords, i
     if (w >= nwords) return;
     const int row = static_cast<int>((w / nkb) % np64);
     if (row >= S) { keep[w] = ~0ull; return; }
-    const uint32_t add = (256u - thresh8) * 0x00010001u;
+    // bit-sliced comparison: 8 hashes are the 8 bit-planes of 32 independent 8-bit random values v; keep iff v >= thresh8
+    // (MSB-first comparator: ~2 logic ops per plane for 32 decisions, instead of a byte-wise compare per hash)
     const uint32_t base = static_cast<uint32_t>(w) * 16u;
     uint32_t word[2];
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-        uint32_t acc = 0;
+        uint32_t ge = 0u, eq = 0xffffffffu;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const uint32_t h = mix32((base + half * 8 + j) ^ seed);
-            const uint32_t de = ((h & 0x00ff00ffu) + add) & 0x01000100u;         // bytes 0, 2 -> bits 8, 24
-            const uint32_t dd = (((h >> 8) & 0x00ff00ffu) + add) & 0x01000100u;  // bytes 1, 3 -> bits 8, 24
-            acc |= (de >> (8 - j)) | (dd << j);  // bits {j, 16+j} and {8+j, 24+j}: every bit of the word used once
+        for (int b = 7; b >= 0; --b) {
+            const uint32_t plane = mix32((base + half * 8 + b) ^ seed);
+            const uint32_t tb = 0u - ((thresh8 >> b) & 1u);  // all ones when the threshold bit is set
+            ge |= eq & plane & ~tb;                            // threshold bit 0, value bit 1: greater
+            eq &= ~(plane ^ tb);                               // still equal on this bit
         }
-        word[half] = acc;
+        word[half] = ge | eq;
     }
     keep[w] = static_cast<unsigned long long>(word[0]) | (static_cast<unsigned long long>(word[1]) << 32);
 }
@@ -117,13 +116,18 @@ __device__ __forceinline__ void fwd_block(const AttnParams& p, float (&o)[8][4],
         o[nt][2] *= alpha[1]; o[nt][3] *= alpha[1];
     }
     if (p.drop_scale != 0.f) {
+        // the lane's bits sit at 8*nt + 2*t + {0, 1}: shift by 2*t once, then every test is at a compile-time position.
+        // The 1/(1-p) factor is NOT applied here: it is folded into the final 1/l normalisation of the output row.
+        const uint32_t alo = static_cast<uint32_t>(keep_a >> (2 * t)), ahi = static_cast<uint32_t>(keep_a >> (2 * t + 32));
+        const uint32_t clo = static_cast<uint32_t>(keep_c >> (2 * t)), chi = static_cast<uint32_t>(keep_c >> (2 * t + 32));
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
-            const int bit = nt * 8 + 2 * t;
-            s[nt][0] = ((keep_a >> bit) & 1ull) ? s[nt][0] * p.drop_scale : 0.f;
-            s[nt][1] = ((keep_a >> (bit + 1)) & 1ull) ? s[nt][1] * p.drop_scale : 0.f;
-            s[nt][2] = ((keep_c >> bit) & 1ull) ? s[nt][2] * p.drop_scale : 0.f;
-            s[nt][3] = ((keep_c >> (bit + 1)) & 1ull) ? s[nt][3] * p.drop_scale : 0.f;
+            const uint32_t wa = nt < 4 ? alo : ahi, wc = nt < 4 ? clo : chi;
+            const int sh = 8 * (nt & 3);
+            s[nt][0] = ((wa >> sh) & 1u) ? s[nt][0] : 0.f;
+            s[nt][1] = ((wa >> (sh + 1)) & 1u) ? s[nt][1] : 0.f;
+            s[nt][2] = ((wc >> sh) & 1u) ? s[nt][2] : 0.f;
+            s[nt][3] = ((wc >> (sh + 1)) & 1u) ? s[nt][3] : 0.f;
         }
     }
     uint32_t pf[4][4];
@@ -193,7 +197,8 @@ attn_fwd_head_kernel(const AttnParams p, const int nkb) {
                 fwd_block(p, o, m, l, qf, base + (nkb + kb) * kTileBytes, base + (2 * nkb + kb) * kTileBytes,
                           sb + kb * kBlk, kb, kvalid, qrow0, bh, nkb, lane, sc2);
             }
-            const float inv0 = 1.f / l[0], inv1 = 1.f / l[1];
+            const float dscale = p.drop_scale != 0.f ? p.drop_scale : 1.f;  // survivors' 1/(1-p), see fwd_block
+            const float inv0 = dscale / l[0], inv1 = dscale / l[1];
             store_acc(p.ctx + static_cast<long long>(b) * S * p.H + h * kHd, p.H, qrow0, S, o, lane, inv0, inv1);
             if (t == 0 && p.lse != nullptr) {
                 float* lse = p.lse + static_cast<long long>(item) * S;
