@@ -206,8 +206,11 @@ def run_ours(args):
     host = synthetic.make_batch(B, c["T"], c["V"], c["Dv"], head=c["head"], seed=1234 + rank,
                                 nlvr_types=(c["head"] == "nlvr"))
     host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()}
-    resident = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host.items()}
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
+    from visualbert_b200.parallel import BatchPrefetcher
+    pf = BatchPrefetcher(dev)  # also ships the indices of the MLM targets (found on the host): no host sync in forward
+    resident = pf.take(pf.stage(host))
+    torch.cuda.synchronize()
+    h2d_bytes = sum(v.numel() * v.element_size() for v in resident.values() if torch.is_tensor(v))
 
     def step(batch):
         sync.zero()
@@ -258,17 +261,28 @@ def run_ours(args):
 
     # ---- end to end: host (pinned) inputs, H2D + loss D2H inside the timed region ----
     # every step copies ITS inputs from pinned host memory (BatchPrefetcher: on a copy stream, overlapping the previous
-    # step) and reads the loss back; K copies and K loss reads happen inside the timed region.
-    from visualbert_b200.parallel import BatchPrefetcher
-    pf = BatchPrefetcher(dev)
+    # step) and reads ITS loss back (asynchronously into pinned memory; the value is consumed one step later, the way a
+    # training loop logs it, so the host never drains the GPU queue). K input copies and K loss reads per K steps, all
+    # inside the timed region.
+    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
 
     def e2e_loop(steps):
         staged = pf.stage(host)                      # step 0's inputs: not overlapped with anything
+        pending, seen = None, 0.0
         for i in range(steps):
             batch = pf.take(staged)
             if i + 1 < steps:
                 staged = pf.stage(host)              # step i+1's inputs, in flight while step i computes
-            float(step(batch).item())
+            loss = step(batch)
+            if pending is not None:
+                pending.synchronize()                # step i-1's loss has long arrived
+                seen += float(loss_host[(i - 1) & 1])
+            loss_host[i & 1].copy_(loss.detach().float(), non_blocking=True)
+            pending = torch.cuda.Event()
+            pending.record()
+        pending.synchronize()
+        seen += float(loss_host[(steps - 1) & 1])
+        return seen
 
     e2e_loop(2)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -271,3 +271,17 @@ def test_batch_prefetcher_matches_direct_copy():
             staged = pf.stage(hosts[i + 1])
         assert batch["tag"] == i
         assert torch.equal(batch["a"].cpu(), hosts[i]["a"]) and torch.equal(batch["b"].cpu(), hosts[i]["b"])
+
+
+def test_masked_lm_rows_extension_gives_identical_results():
+    """forward(masked_lm_rows=...) (indices found on the host by BatchPrefetcher) == the default device-side scan."""
+    from visualbert_b200.parallel import BatchPrefetcher
+    model, cfg, sd, batch, c, gold = _build("small_ragged_pretraining")
+    host = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    rows = BatchPrefetcher.labelled_rows(host).to("cuda:0")
+    a = model(**batch)
+    b = model(**batch, masked_lm_rows=rows)
+    assert a["loss"].item() == b["loss"].item() and a["masked_lm_loss"].item() == b["masked_lm_loss"].item()
+    staged = BatchPrefetcher("cuda:0").stage({k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()})
+    c2 = model(**BatchPrefetcher("cuda:0").take(staged))
+    assert c2["loss"].item() == a["loss"].item()

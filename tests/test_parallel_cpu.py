@@ -90,3 +90,18 @@ def test_flat_grad_layout_keeps_qkv_adjacent_and_everything_else_aligned():
     for p in model.parameters():
         if p.requires_grad:
             assert (p.grad.data_ptr() - base) % 16 == 0, "16-byte vector access must stay legal"
+
+
+def test_host_side_mlm_rows_equal_the_padded_label_scan():
+    """BatchPrefetcher.labelled_rows (host) == nonzero over the labels padded with -1 on the region positions, which is
+    what TrainVisualBERTObjective.forward scans on the device when `masked_lm_rows` is not given."""
+    sys.path.insert(0, ROOT)
+    from visualbert_b200 import synthetic
+    from visualbert_b200.parallel import BatchPrefetcher
+    for choices in (None, 3):
+        b = synthetic.make_batch(5, 12, 7, 16, head="pretraining", vocab=512, ragged=True, choices=choices)
+        labels = b["masked_lm_labels"].reshape(-1, 12)
+        padded = torch.cat((labels, torch.full((labels.shape[0], 7), -1, dtype=labels.dtype)), dim=1)
+        want = torch.nonzero(padded.reshape(-1) != -1).squeeze(1)
+        assert torch.equal(BatchPrefetcher.labelled_rows(b), want)
+    assert BatchPrefetcher.labelled_rows({"input_ids": torch.zeros(2, 3)}) is None

@@ -618,7 +618,11 @@ class TrainVisualBERTObjective(PreTrainedBertModel):
     def forward(self, input_ids, token_type_ids, input_mask, visual_embeddings, position_embeddings_visual, image_mask,
                 image_text_alignment=None, confidence=None, visual_embeddings_type=None, label=None,
                 flickr_position=None, masked_lm_labels=None, image_lm_lables=None, is_random_next=None,
-                output_all_encoded_layers=False):
+                output_all_encoded_layers=False, masked_lm_rows=None):
+        """Reference signature (M.py:1373-1392) plus one optional extension: `masked_lm_rows`, the flat indices
+        (b * (T + V) + t, int64, on the device) of the positions whose `masked_lm_labels` is not -1. When given (e.g. by
+        `parallel.BatchPrefetcher`, which computes them on the host from the host copy of the labels) the forward pass
+        contains no host synchronisation at all; when omitted they are found with one `nonzero` before the encoder."""
         flat_input_ids = transform_to_batch_sequence(input_ids)
         flat_token_type_ids = transform_to_batch_sequence(token_type_ids)
         flat_input_mask = transform_to_batch_sequence(input_mask)
@@ -646,8 +650,9 @@ class TrainVisualBERTObjective(PreTrainedBertModel):
         else:
             flat_attention_mask = flat_input_mask
 
-        mlm_rows = None
-        if self.training_head_type == "pretraining" and flat_masked_lm_labels is not None and not output_all_encoded_layers:
+        mlm_rows = masked_lm_rows
+        if (mlm_rows is None and self.training_head_type == "pretraining" and flat_masked_lm_labels is not None
+                and not output_all_encoded_layers):
             mlm_rows = self._labelled_rows(flat_masked_lm_labels)  # the only host sync of the step: do it up front
         if self.output_attention_weights:
             # analysis mode (M.py:1430-1444): nothing but the per-layer attention maps is returned

@@ -98,11 +98,30 @@ class BatchPrefetcher:
             loss = step(batch)
     """
 
-    def __init__(self, device):
+    def __init__(self, device, mlm_rows=True):
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(device=self.device)
+        self.mlm_rows = mlm_rows
+
+    @staticmethod
+    def labelled_rows(host_batch):
+        """Flat indices b * (T + V) + t of the MLM targets, from the HOST copy of the labels (what
+        TrainVisualBERTObjective.forward accepts as `masked_lm_rows`): finding them on the device costs a host sync."""
+        labels = host_batch.get("masked_lm_labels")
+        if labels is None or labels.is_cuda:
+            return None
+        vis = host_batch.get("visual_embeddings")
+        T = labels.shape[-1]
+        V = 0 if vis is None else vis.shape[-2]
+        flat = labels.reshape(-1, T)
+        b, t = torch.nonzero(flat != -1, as_tuple=True)
+        return (b * (T + V) + t).to(torch.int64)
 
     def stage(self, host_batch):
+        if self.mlm_rows and "masked_lm_rows" not in host_batch:
+            rows = self.labelled_rows(host_batch)
+            if rows is not None:
+                host_batch = dict(host_batch, masked_lm_rows=rows.pin_memory())
         with torch.cuda.stream(self.stream):
             dev = {k: (v.to(self.device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host_batch.items()}
             ev = torch.cuda.Event()
