@@ -266,22 +266,30 @@ def run_ours(args):
     # inside the timed region.
     loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
 
+    diag = os.environ.get("VB_BENCH_E2E_DIAG", "")  # "nocopy" / "noloss": diagnostics only, never a reported number
+    enq = [0.0, 0]
+
     def e2e_loop(steps):
         staged = pf.stage(host)                      # step 0's inputs: not overlapped with anything
         pending, seen = None, 0.0
         for i in range(steps):
-            batch = pf.take(staged)
-            if i + 1 < steps:
+            t0 = time.perf_counter()
+            batch = pf.take(staged) if diag != "nocopy" else resident
+            if i + 1 < steps and diag != "nocopy":
                 staged = pf.stage(host)              # step i+1's inputs, in flight while step i computes
             loss = step(batch)
+            enq[0] += time.perf_counter() - t0; enq[1] += 1
+            if diag == "noloss":
+                continue
             if pending is not None:
                 pending.synchronize()                # step i-1's loss has long arrived
                 seen += float(loss_host[(i - 1) & 1])
             loss_host[i & 1].copy_(loss.detach().float(), non_blocking=True)
             pending = torch.cuda.Event()
             pending.record()
-        pending.synchronize()
-        seen += float(loss_host[(steps - 1) & 1])
+        if pending is not None:
+            pending.synchronize()
+            seen += float(loss_host[(steps - 1) & 1])
         return seen
 
     e2e_loop(2)
@@ -356,7 +364,7 @@ def run_ours(args):
                           "note": "hot-path algorithmic FLOPs (SURVEY.md §8d, heads and recompute not credited) over the whole step"},
         "kernel_ms_per_step": kern_ms,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d_bytes),
-                "d2h_bytes_per_step": 4},
+                "d2h_bytes_per_step": 4, "host_enqueue_ms_per_step": round(1e3 * enq[0] / max(1, enq[1]), 3)},
     }
     if opt_info is not None:
         line["optimizer"] = opt_info
