@@ -83,11 +83,10 @@ ln_fwd_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict
 // when its output went through dropout before the residual add; dx itself continues down the
 // residual branch).
 //
-// HBM-bound, so the design goal is bytes in flight: the row is kept as packed bf16 (2 x 16 B per
-// chunk) and unpacked twice instead of living as fp32, gamma and the three column accumulators live
-// in shared memory (one private slab per warp: plain float4 read-modify-write, no atomics, no bank
-// conflicts thanks to the split lo/hi float4 layout), which brings the kernel to ~80 registers and
-// 3 blocks (24 warps, 144 x 512 B loads in flight) per SM.
+// Nominally HBM-bound, in practice instruction-issue bound (IPC 2.5, ~50 % of HBM peak): the row is unpacked once and
+// xhat / dy stay in fp32 registers for both passes; gamma and the three column accumulators live in shared memory (one
+// private slab per warp: plain float4 read-modify-write, no atomics, no bank conflicts thanks to the split lo/hi
+// float4 layout); 123 registers, 2 blocks (16 warps) per SM.
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
     f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
@@ -102,7 +101,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 __device__ __forceinline__ int slot(int a, int h, int ch, int chunks) { return (a * 2 + h) * chunks + ch; }
 
 template <int NC>
-__global__ void __launch_bounds__(kLnWarps * 32, 3)
+__global__ void __launch_bounds__(kLnWarps * 32, 2)
 ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ gamma, bf16* __restrict__ dx,
               bf16* __restrict__ dx_drop, float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -125,74 +124,71 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
 
     const float invH = 1.0f / H;
     for (int row = blockIdx.x * kLnWarps + warp; row < rows; row += gridDim.x * kLnWarps) {
+        const long long rbase = static_cast<long long>(row) * H;
+        const unsigned long long e8row = static_cast<unsigned long long>(row) * static_cast<unsigned>(chunks);
         uint4 ux[NC], ud[NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             const int ch = lane + c * 32;
             if (ch < chunks) {
-                ux[c] = ldg_v4(x + static_cast<long long>(row) * H + ch * 8);
-                ud[c] = ldg_v4(dy + static_cast<long long>(row) * H + ch * 8);
+                ux[c] = ldg_v4(x + rbase + ch * 8);
+                ud[c] = ldg_v4(dy + rbase + ch * 8);
             }
         }
         const float mu = mean[row], rs = rstd[row];
+        const float nmr = -mu * rs;
+        // the row is unpacked ONCE: xh = xhat and dv = dy stay in fp32 registers for both passes (the kernel is
+        // instruction-issue bound, not register/occupancy bound: profiles/r01final_layer_kernels.md)
+        float xh[NC][8], dv[NC][8];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             const int ch = lane + c * 32;
             if (ch < chunks) {
-                float xv[8], dv[8];
-                unpack8(ux[c], xv);
-                unpack8(ud[c], dv);
+                unpack8(ux[c], xh[c]);
+                unpack8(ud[c], dv[c]);
                 if (in_scale != 0.f) {  // dy is the gradient of dropout(LN(x)): re-apply the keep mask
-                    const unsigned long long e8 = (static_cast<unsigned long long>(row) * static_cast<unsigned>(H) + ch * 8) >> 3;
-                    const uint32_t keep = dropout_keep8(drop_seed, in_stream, e8, in_thresh16);
+                    const uint32_t keep = dropout_keep8(drop_seed, in_stream, e8row + ch, in_thresh16);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) dv[i] = ((keep >> i) & 1u) ? dv[i] * in_scale : 0.f;
+                    for (int i = 0; i < 8; ++i) dv[c][i] = ((keep >> i) & 1u) ? dv[c][i] * in_scale : 0.f;
                 }
                 const float4 g0 = sgam[ch], g1 = sgam[chunks + ch];
                 const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float g = dv[i] * gm[i];
+                    xh[c][i] = fmaf(xh[c][i], rs, nmr);  // xhat
+                    const float g = dv[c][i] * gm[i];
                     s1 += g;
-                    s2 += g * ((xv[i] - mu) * rs);
+                    s2 = fmaf(g, xh[c][i], s2);
                 }
             }
         }
         const float c1 = warp_sum(s1) * invH, c2 = warp_sum(s2) * invH;
+        const float rc1 = rs * c1, rc2 = rs * c2;
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             const int ch = lane + c * 32;
             if (ch < chunks) {
-                float xv[8], dv[8], o[8];
-                unpack8(ux[c], xv);
-                unpack8(ud[c], dv);
-                if (in_scale != 0.f) {
-                    const unsigned long long e8 = (static_cast<unsigned long long>(row) * static_cast<unsigned>(H) + ch * 8) >> 3;
-                    const uint32_t keep = dropout_keep8(drop_seed, in_stream, e8, in_thresh16);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) dv[i] = ((keep >> i) & 1u) ? dv[i] * in_scale : 0.f;
-                }
                 const float4 g0 = sgam[ch], g1 = sgam[chunks + ch];
                 const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                float o[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    xv[i] = (xv[i] - mu) * rs;  // xhat
-                    o[i] = rs * (dv[i] * gm[i] - c1 - xv[i] * c2);
-                }
-                stg_v4(dx + static_cast<long long>(row) * H + ch * 8, pack8(o));
+                for (int i = 0; i < 8; ++i)  // rs * (g - c1 - xhat * c2)
+                    o[i] = fmaf(-xh[c][i], rc2, fmaf(dv[c][i] * gm[i], rs, -rc1));
+                stg_v4(dx + rbase + ch * 8, pack8(o));
                 if (dx_drop != nullptr) {
-                    const unsigned long long e8 = (static_cast<unsigned long long>(row) * static_cast<unsigned>(H) + ch * 8) >> 3;
-                    const uint32_t keep = dropout_keep8(drop_seed, drop_stream, e8, drop_thresh16);
+                    const uint32_t keep = dropout_keep8(drop_seed, drop_stream, e8row + ch, drop_thresh16);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) o[i] = ((keep >> i) & 1u) ? o[i] * drop_scale : 0.f;
-                    stg_v4(dx_drop + static_cast<long long>(row) * H + ch * 8, pack8(o));
+                    stg_v4(dx_drop + rbase + ch * 8, pack8(o));
                 }
+                const float* d = dv[c];
+                const float* h = xh[c];
                 float4 a;
-                a = acc[slot(0, 0, ch, chunks)]; a.x += dv[0] * xv[0]; a.y += dv[1] * xv[1]; a.z += dv[2] * xv[2]; a.w += dv[3] * xv[3]; acc[slot(0, 0, ch, chunks)] = a;
-                a = acc[slot(0, 1, ch, chunks)]; a.x += dv[4] * xv[4]; a.y += dv[5] * xv[5]; a.z += dv[6] * xv[6]; a.w += dv[7] * xv[7]; acc[slot(0, 1, ch, chunks)] = a;
-                a = acc[slot(1, 0, ch, chunks)]; a.x += dv[0]; a.y += dv[1]; a.z += dv[2]; a.w += dv[3]; acc[slot(1, 0, ch, chunks)] = a;
-                a = acc[slot(1, 1, ch, chunks)]; a.x += dv[4]; a.y += dv[5]; a.z += dv[6]; a.w += dv[7]; acc[slot(1, 1, ch, chunks)] = a;
+                a = acc[slot(0, 0, ch, chunks)]; a.x = fmaf(d[0], h[0], a.x); a.y = fmaf(d[1], h[1], a.y); a.z = fmaf(d[2], h[2], a.z); a.w = fmaf(d[3], h[3], a.w); acc[slot(0, 0, ch, chunks)] = a;
+                a = acc[slot(0, 1, ch, chunks)]; a.x = fmaf(d[4], h[4], a.x); a.y = fmaf(d[5], h[5], a.y); a.z = fmaf(d[6], h[6], a.z); a.w = fmaf(d[7], h[7], a.w); acc[slot(0, 1, ch, chunks)] = a;
+                a = acc[slot(1, 0, ch, chunks)]; a.x += d[0]; a.y += d[1]; a.z += d[2]; a.w += d[3]; acc[slot(1, 0, ch, chunks)] = a;
+                a = acc[slot(1, 1, ch, chunks)]; a.x += d[4]; a.y += d[5]; a.z += d[6]; a.w += d[7]; acc[slot(1, 1, ch, chunks)] = a;
                 a = acc[slot(2, 0, ch, chunks)]; a.x += o[0]; a.y += o[1]; a.z += o[2]; a.w += o[3]; acc[slot(2, 0, ch, chunks)] = a;
                 a = acc[slot(2, 1, ch, chunks)]; a.x += o[4]; a.y += o[5]; a.z += o[6]; a.w += o[7]; acc[slot(2, 1, ch, chunks)] = a;
             }
@@ -242,7 +238,9 @@ int ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, 
     VB_REQUIRE(rows > 0, "layernorm backward: no rows");
     VB_REQUIRE((dropout_p > 0.f) == (dx_drop != nullptr), "layernorm backward: dx_drop iff dropout_p > 0");
     const int nc = (H / 8 + 31) / 32;
-    int grid = num_sms() * 3;
+    // 2 resident blocks per SM (123 registers: the row is cached in fp32; an 80-register / 3-block build spills and
+    // measured 30 % slower)
+    int grid = num_sms() * 2;
     const int need = (rows + kLnWarps - 1) / kLnWarps;
     if (grid > need) grid = need;
     const DropQ dq = dropout_quantise(dropout_p), iq = dropout_quantise(in_dropout_p);
