@@ -110,6 +110,8 @@ class ClockSampler:
 
 def build_cfg(name, batch_override=None):
     c = dict(synthetic.CONFIGS[name])
+    c["index"] = int(name[3:]) - 1
+    c["B"] = c["B"] // c.pop("dp", 1)  # per-GPU batch: BASELINE.json quotes configs[2..4] as global batches over 8 GPUs
     if batch_override:
         c["B"] = batch_override
     return c
@@ -169,7 +171,7 @@ def run_reference(args):
 
 def workload_name(c):
     return (f"VisualBERT L{c['layers']}/H{c['hidden']} {c['head']} step, {c['V']} regions x {c['Dv']}-d + {c['T']} tokens "
-            f"(BASELINE.json configs[1])")
+            f"(BASELINE.json configs[{c.get('index', 1)}])")
 
 
 def run_ours(args):
