@@ -386,7 +386,10 @@ class PreTrainedBertModel(nn.Module):
         if not os.path.isdir(path):
             tempdir = tempfile.mkdtemp()
             with tarfile.open(path, "r:gz") as archive:
-                archive.extractall(tempdir)
+                try:
+                    archive.extractall(tempdir, filter="data")  # refuse absolute paths / links escaping the directory
+                except TypeError:  # Python < 3.12
+                    archive.extractall(tempdir)
             path = tempdir
         try:
             config = BertConfig.from_json_file(os.path.join(path, CONFIG_NAME))
@@ -405,7 +408,16 @@ class PreTrainedBertModel(nn.Module):
         for k, v in state_dict.items():
             nk = k[:-5] + "weight" if k.endswith("gamma") else (k[:-4] + "bias" if k.endswith("beta") else k)
             renamed[nk] = v
-        target = model if not hasattr(model, "bert") or any(k.startswith("bert.") for k in renamed) else model.bert
+        # prefix rule of the reference (M.py:585): a bare encoder (no `.bert` attribute) reads its weights from the
+        # "bert."-prefixed entries of the checkpoint; a wrapper model takes the keys as they are (and, more lenient than
+        # the reference, a checkpoint of the bare encoder is accepted for the wrapper's `.bert`)
+        has_prefix = any(k.startswith("bert.") for k in renamed)
+        if not hasattr(model, "bert"):
+            target = model
+            if has_prefix:
+                renamed = {k[5:]: v for k, v in renamed.items() if k.startswith("bert.")}
+        else:
+            target = model if has_prefix else model.bert
         result = target.load_state_dict(renamed, strict=False)
         missing = [k for k in result.missing_keys if k != "cls.predictions.decoder.weight"]
         if missing:
