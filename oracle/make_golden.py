@@ -40,6 +40,11 @@ CASES = {
                               batch=dict(B=4, T=10, V=8, ragged=True, nlvr_types=True), flags=dict(bypass_transformer=True)),
     "small_attention_weights": dict(model=dict(layers=2, hidden=128, heads=2, inter=512, vocab=512), Dv=64, head="nlvr",
                                     batch=dict(B=3, T=10, V=6, ragged=True), flags=dict(output_attention_weights=True)),
+    # the two remaining task heads of TrainVisualBERTObjective (M.py:1527-1554, 1568-1598)
+    "small_vqa_advanced": dict(model=dict(layers=2, hidden=128, heads=2, inter=512, vocab=512), Dv=64, head="vqa_advanced",
+                               batch=dict(B=3, T=12, V=7, ragged=True)),
+    "small_flickr": dict(model=dict(layers=2, hidden=128, heads=2, inter=512, vocab=512), Dv=64, head="flickr",
+                         batch=dict(B=3, T=12, V=7, ragged=True)),
     "base3_ragged_pretraining": dict(model=dict(layers=3, hidden=768, heads=12, inter=3072, vocab=2048), Dv=2048,
                                      head="pretraining", batch=dict(B=5, T=33, V=19, ragged=True)),
 }
@@ -105,7 +110,10 @@ def main():
         for k in ("masked_lm_loss", "next_sentence_loss"):
             if k in out:
                 rec[k] = np.float64(out[k].item())
-        logits = out["logits"]
+        for k in ("accuracy", "upperbound_accuracy", "entity_num"):
+            if k in out and out[k] is not None:
+                rec[k] = np.float64(float(out[k]))
+        logits = out["logits"] if "logits" in out else loss.detach().reshape(1)  # the flickr head returns no logits
         rec["logits_sub"] = subsample(logits)
         rec["logits_stats"] = np.array([logits.double().mean().item(), logits.double().std().item(),
                                         logits.double().abs().max().item()])

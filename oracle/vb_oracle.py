@@ -142,7 +142,7 @@ def pretraining_heads(sd, seq, pooled):
 
 def objective(sd, cfg, head, input_ids, token_type_ids, input_mask, visual_embeddings, image_mask,
               visual_embeddings_type=None, label=None, masked_lm_labels=None, is_random_next=None,
-              image_text_alignment=None, bypass_transformer=False, output_attention_weights=False):
+              image_text_alignment=None, bypass_transformer=False, output_attention_weights=False, flickr_position=None):
     """TrainVisualBERTObjective.forward, M.py:1373-1598 for heads pretraining / vqa / nlvr /
     multichoice, eval mode (dropout off). Returns the reference's output dict."""
     ids, tt, im = _flat2(input_ids), _flat2(token_type_ids), _flat2(input_mask)
@@ -189,6 +189,32 @@ def objective(sd, cfg, head, input_ids, token_type_ids, input_mask, visual_embed
         out["logits"], out["loss"] = logits, None
         if label is not None:
             out["loss"] = F.cross_entropy(logits, label)
+    elif head == "vqa_advanced":  # M.py:1527-1554: answer tokens predicted by the MLM head; accuracy = all labelled right
+        logits, nsp = pretraining_heads(sd, seq, pooled)
+        out["logits"], out["seq_relationship_score"] = logits, nsp
+        mlm = F.cross_entropy(logits.view(-1, logits.size(-1)), lab.view(-1), ignore_index=-1)
+        out["masked_lm_loss"] = out["loss"] = mlm
+        pred = logits.argmax(-1)
+        ok = ((lab == -1) | (pred == lab)).all(dim=1)
+        out["accuracy"] = float(ok.sum().item()) / pred.size(0)
+    elif head == "flickr":  # M.py:1568-1598 with FlickrAttention M.py:1602-1646
+        out["loss"] = None
+        if flickr_position is not None:
+            pmask = (flickr_position != -1).long()
+            entities = pmask.view(-1).sum(-1)
+            pos = flickr_position * pmask
+            sel = seq.gather(1, pos.unsqueeze(2).expand(pos.size(0), pos.size(1), seq.size(2)))   # M.py:1713-1716
+            vis = seq[:, im.size(1):, :]
+            d = sd["flickr_attention.query.weight"].size(0)
+            q, k = linear(sel, sd, "flickr_attention.query"), linear(vis, sd, "flickr_attention.key")
+            scores = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(d) + ((1.0 - vm.to(seq.dtype)) * -10000.0)[:, None, :]
+            logp = torch.log_softmax(scores, dim=-1)
+            out["loss"] = F.kl_div(logp, label, reduction="batchmean")
+            lmask = (label != 0.0).to(seq.dtype)                                                  # M.py:1651-1653
+            hit = lmask.gather(2, logp.argmax(-1, keepdim=True)).view(-1).sum(-1)                 # M.py:1671-1675
+            out["accuracy"] = hit / entities
+            out["upperbound_accuracy"] = label.sum(-1).view(-1).sum(-1) / entities
+            out["entity_num"] = entities
     else:
         raise ValueError(head)
     return out

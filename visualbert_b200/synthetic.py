@@ -75,6 +75,10 @@ def param_shapes(cfg, head, visual_dim, bypass_transformer=False):
         s["classifier.weight"], s["classifier.bias"] = (3129, H), (3129,)
     elif head == "nlvr":
         s["classifier.weight"], s["classifier.bias"] = (2, H), (2,)
+    if head == "flickr":
+        d = H // cfg["num_attention_heads"]
+        for n in ("query", "key", "value"):
+            s[f"flickr_attention.{n}.weight"], s[f"flickr_attention.{n}.bias"] = (d, H), (d,)
     if bypass_transformer:
         _layer_shapes(s, "bert.additional_layer.", H, I)
     return s
@@ -142,6 +146,20 @@ def make_batch(B, T, V, Dv, head="pretraining", seed=1234, ragged=False, vocab=3
         batch["label"] = torch.randint(0, 2, (n,), generator=g)
     elif head == "multichoice":
         batch["label"] = torch.randint(0, choices or 4, (B,), generator=g)
+    elif head == "vqa_advanced":  # answers as masked tokens (M.py:1527-1554): MLM labels only
+        sel = (torch.rand(n, T, generator=g) < 0.15) & (input_mask == 1)
+        sel[:, 1] = True
+        batch["masked_lm_labels"] = torch.where(sel, ids, torch.full_like(ids, -1)).view(*lead, T)
+    elif head == "flickr":  # phrase grounding (M.py:1568-1598): entity token positions and soft region targets
+        E = 4
+        pos = torch.stack([torch.randint(1, max(2, int(tl[i])), (E,), generator=g) for i in range(n)])
+        n_ent = torch.randint(1, E + 1, (n,), generator=g)
+        pos = torch.where(torch.arange(E).unsqueeze(0) < n_ent.unsqueeze(1), pos, torch.full_like(pos, -1))
+        tgt = (torch.rand(n, E, V, generator=g) < 0.3).float() * image_mask.unsqueeze(1).float()
+        tgt[:, :, 0] = 1.0  # every entity has at least one target region (region 0 is always valid)
+        tgt = tgt * (pos != -1).unsqueeze(-1).float()
+        batch["flickr_position"] = pos
+        batch["label"] = tgt / tgt.sum(-1, keepdim=True).clamp(min=1.0)
     if alignment:
         ali = torch.randint(0, T, (n, V, alignment), generator=g)
         ali = torch.where(torch.rand(n, V, alignment, generator=g) < 0.4, torch.full_like(ali, -1), ali)
