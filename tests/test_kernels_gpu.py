@@ -221,9 +221,9 @@ def test_attention_dropout_consistent_between_fwd_and_bwd():
     assert abs(ctx.float().mean().item() - ref.mean().item()) < 5e-3
 
 
-@pytest.mark.parametrize("impl", ["tc", "staged"])
+@pytest.mark.parametrize("impl", ["head", "staged"])
 def test_attention_alternative_implementations(impl):
-    """The tcgen05/TMEM forward kernel and the generic staged kernels must agree with the default whole-head kernels
+    """The whole-head mma.sync kernels and the generic staged kernels must agree with the default tcgen05 kernels
     (selected per process through VB_ATTN_FWD_IMPL / VB_ATTN_STAGED, so each runs in a subprocess)."""
     import os, subprocess, sys
     env = dict(os.environ)

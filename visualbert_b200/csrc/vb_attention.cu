@@ -475,23 +475,24 @@ int attn_fwd(const void* qkv, const float* mask_bias, void* ctx, float* lse, voi
     int rc = fill_params(p, qkv, mask_bias, ctx, lse, nullptr, nullptr, nullptr, keep, B, S, A, H, dropout_p, seed, stream_id);
     if (rc) return rc;
     dim3 grid((S + kBlk - 1) / kBlk, A, B);
-    // implementation choice (VB_ATTN_FWD_IMPL = head | tc | staged): the persistent whole-head mma.sync kernel is
-    // the default — measured 238 us/layer at the benchmark shape vs 298 us for the tcgen05 kernel, whose single
-    // softmax warp-group per SM is still latency-bound; the staged kernel handles seq > 256.
+    // implementation choice (VB_ATTN_FWD_IMPL = tc | head | staged): the tcgen05 / TMEM / TMA kernel is the default
+    // for seq <= 192 (every reference config), the persistent whole-head mma.sync kernel covers seq <= 256, the
+    // staged kernel any length.
     static int impl = -1;
     if (impl < 0) {
         const char* e = getenv("VB_ATTN_FWD_IMPL");
-        impl = e == nullptr ? 1 : (e[0] == 't' ? 0 : (e[0] == 's' ? 2 : 1));
+        impl = e == nullptr ? 0 : (e[0] == 't' ? 0 : (e[0] == 's' ? 2 : 1));
     }
-    if (impl == 0 && !staged_only() && attn_fwd_tc_supported(p)) return attn_fwd_tc(p, st);
+    if (impl == 0 && !staged_only() && attn_fwd_tc_supported(p)) {
+        rc = attn_keep_mask(p, static_cast<int>(grid.x), st);
+        if (rc) return rc;
+        return attn_fwd_tc(p, st);
+    }
     if (impl <= 1 && static_cast<int>(grid.x) <= kMaxSub && !staged_only()) return attn_fwd_head(p, static_cast<int>(grid.x), st);
     const int nsub = static_cast<int>(grid.x) < kMaxSub ? static_cast<int>(grid.x) : kMaxSub;
     const int smem = (1 + 2 * nsub) * kTileBytes;
-    static bool configured = false;
-    if (!configured) {
-        VB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 + 2 * kMaxSub) * kTileBytes));
-        configured = true;
-    }
+    static int configured[kMaxDevices] = {0};
+    VB_CHECK_CUDA(ensure_dyn_smem(attn_fwd_kernel<1, 3>, (1 + 2 * kMaxSub) * kTileBytes, configured));
     {
         ProfScope ps(st, PROF_ATTN_FWD, 4.0 * B * A * S * S * kHd, 1);
         attn_fwd_kernel<1, 3><<<grid, 128, smem, st>>>(p, nsub);
@@ -509,15 +510,16 @@ int attn_bwd(const void* qkv, const float* mask_bias, const void* ctx, const flo
     int rc = fill_params(p, qkv, mask_bias, const_cast<void*>(ctx), const_cast<float*>(lse), dctx, dqkv, drow,
                          const_cast<void*>(keep), B, S, A, H, dropout_p, seed, stream_id);
     if (rc) return rc;
-    static bool configured = false;
-    if (!configured) {
-        VB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (3 + 2 * kMaxSub) * kTileBytes));
-        VB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (3 + 2 * kMaxSub) * kTileBytes));
-        VB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 + 2 * kMaxSub) * kTileBytes));
-        VB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 + 2 * kMaxSub) * kTileBytes));
+    static int c0[kMaxDevices] = {0}, c1[kMaxDevices] = {0}, c2[kMaxDevices] = {0}, c3[kMaxDevices] = {0};
+    VB_CHECK_CUDA(ensure_dyn_smem(attn_bwd_dq_kernel<2>, (3 + 2 * kMaxSub) * kTileBytes, c0));
+    VB_CHECK_CUDA(ensure_dyn_smem(attn_bwd_dq_kernel<3>, (3 + 2 * kMaxSub) * kTileBytes, c1));
+    VB_CHECK_CUDA(ensure_dyn_smem(attn_bwd_dkv_kernel<2>, (2 + 2 * kMaxSub) * kTileBytes, c2));
+    VB_CHECK_CUDA(ensure_dyn_smem(attn_bwd_dkv_kernel<3>, (2 + 2 * kMaxSub) * kTileBytes, c3));
+    static bool env_read = false;
+    if (!env_read) {
         const char* e = getenv("VB_ATTN_BWD_MINB");  // tuning knob: resident CTAs per SM the backward kernels are compiled for
         if (e != nullptr) g_bwd_minb = atoi(e) == 2 ? 2 : 3;
-        configured = true;
+        env_read = true;
     }
     dim3 grid((S + kBlk - 1) / kBlk, A, B);
     if (static_cast<int>(grid.x) <= kMaxSub && !staged_only()) return attn_bwd_head(p, static_cast<int>(grid.x), st);

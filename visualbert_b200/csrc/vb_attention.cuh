@@ -264,8 +264,10 @@ constexpr int kMaxSub = 4;  // 64-row tiles per resident stage
 // whole-head persistent kernels (vb_attention_head.cu); nkb = ceil(S / 64) <= kMaxSub
 int attn_fwd_head(const AttnParams& p, int nkb, cudaStream_t st);
 int attn_bwd_head(const AttnParams& p, int nkb, cudaStream_t st);
-// tcgen05 / TMEM / TMA forward (vb_attention_tc.cu), seq <= 256
+int attn_keep_mask(const AttnParams& p, int nkb, cudaStream_t st);
+// tcgen05 / TMEM / TMA forward (vb_attention_tc.cu), seq <= 192
 bool attn_fwd_tc_supported(const AttnParams& p);
 int attn_fwd_tc(const AttnParams& p, cudaStream_t st);
+int make_tmap_3d(CUtensorMap* m, const void* ptr, int S, int B, int ld, int box_rows);
 
 }  // namespace vb

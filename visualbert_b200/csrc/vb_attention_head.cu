@@ -610,11 +610,8 @@ attn_bwd_head_ps_kernel(const AttnParams p, const int nkb, const int colsP) {
 template <int NW>
 static int launch_fwd(const AttnParams& p, int nkb, cudaStream_t st) {
     const int smem = 2 * 3 * nkb * kTileBytes + 2 * nkb * kBlk * 4;
-    static int configured = 0;
-    if (configured < smem) {
-        VB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_head_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = smem;
-    }
+    static int configured[kMaxDevices] = {0};
+    VB_CHECK_CUDA(ensure_dyn_smem(attn_fwd_head_kernel<NW>, smem, configured));
     const int total = p.B * p.A;
     const int grid = total < num_sms() ? total : num_sms();
     ProfScope ps(st, PROF_ATTN_FWD, 4.0 * p.B * p.A * p.S * p.S * kHd, 1);
@@ -622,17 +619,22 @@ static int launch_fwd(const AttnParams& p, int nkb, cudaStream_t st) {
     return 0;
 }
 
+// draws the attention-dropout keep bits of the whole layer call (no-op without dropout)
+int attn_keep_mask(const AttnParams& p, int nkb, cudaStream_t st) {
+    if (p.drop_scale == 0.f) return 0;
+    const int np64 = nkb * kBlk;
+    const long long nwords = static_cast<long long>(p.B) * p.A * np64 * nkb;
+    VB_REQUIRE(nwords * 16 < (1LL << 32), "attention dropout: mask counter space exceeded (B*A*S too large)");
+    ProfScope ps(st, PROF_ATTN_FWD, 0.0, 1);
+    VB_CHECK_CUDA(launch_pdl(attn_keep_mask_kernel, dim3(static_cast<unsigned>((nwords + 255) / 256)), dim3(256), 0, st, p.keep,
+                             nwords, nkb, np64, p.S, p.drop_seed, p.drop_thresh16));
+    return 0;
+}
+
 int attn_fwd_head(const AttnParams& p, int nkb, cudaStream_t st) {
     const int nw = (p.S + 15) / 16;
-    int rc;
-    if (p.drop_scale != 0.f) {
-        const int np64 = nkb * kBlk;
-        const long long nwords = static_cast<long long>(p.B) * p.A * np64 * nkb;
-        VB_REQUIRE(nwords * 16 < (1LL << 32), "attention dropout: mask counter space exceeded (B*A*S too large)");
-        ProfScope ps(st, PROF_ATTN_FWD, 0.0, 1);
-        VB_CHECK_CUDA(launch_pdl(attn_keep_mask_kernel, dim3(static_cast<unsigned>((nwords + 255) / 256)), dim3(256), 0, st, p.keep,
-                                 nwords, nkb, np64, p.S, p.drop_seed, p.drop_thresh16));
-    }
+    int rc = attn_keep_mask(p, nkb, st);
+    if (rc) return rc;
     if (nw <= 4) rc = launch_fwd<4>(p, nkb, st);
     else if (nw <= 8) rc = launch_fwd<8>(p, nkb, st);
     else if (nw <= 12) rc = launch_fwd<12>(p, nkb, st);
@@ -647,11 +649,8 @@ static int launch_bwd(const AttnParams& p, int nkb, cudaStream_t st) {
     const int per_buf = 4 * nkb * kTileBytes + 3 * nkb * kBlk * 4;
     const int nbuf = 2 * per_buf <= 200 * 1024 ? 2 : 1;
     const int smem = nbuf * per_buf;
-    static int configured = 0;
-    if (configured < smem) {
-        VB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_head_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = smem;
-    }
+    static int configured[kMaxDevices] = {0};
+    VB_CHECK_CUDA(ensure_dyn_smem(attn_bwd_head_kernel<NW>, smem, configured));
     const int total = p.B * p.A;
     const int grid = total < num_sms() ? total : num_sms();
     ProfScope ps(st, PROF_ATTN_DKV, 7.0 * p.B * p.A * p.S * p.S * kHd, 1);
@@ -662,11 +661,8 @@ static int launch_bwd(const AttnParams& p, int nkb, cudaStream_t st) {
 // P/dS-in-shared-memory variant: only when the whole head fits (S <= ~176); VB_ATTN_BWD_PS=0 disables it
 template <int NW>
 static int launch_bwd_ps(const AttnParams& p, int nkb, int colsP, int smem, cudaStream_t st) {
-    static int configured = 0;
-    if (configured < smem) {
-        VB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_head_ps_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = smem;
-    }
+    static int configured[kMaxDevices] = {0};
+    VB_CHECK_CUDA(ensure_dyn_smem(attn_bwd_head_ps_kernel<NW>, smem, configured));
     const int total = p.B * p.A;
     const int grid = total < num_sms() ? total : num_sms();
     ProfScope ps(st, PROF_ATTN_DKV, 5.0 * p.B * p.A * p.S * p.S * kHd, 1);
@@ -675,14 +671,12 @@ static int launch_bwd_ps(const AttnParams& p, int nkb, int colsP, int smem, cuda
 }
 
 static int bwd_ps_smem(const AttnParams& p, int nkb, int* colsP) {
-    static int enabled = -1, max_smem = 0;
+    static int enabled = -1;
     if (enabled < 0) {
         const char* e = getenv("VB_ATTN_BWD_PS");
         enabled = (e && e[0] == '0') ? 0 : 1;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     }
+    const int max_smem = 227 * 1024;  // sm_100a opt-in limit per block (the library targets this arch only)
     if (!enabled) return 0;
     *colsP = (p.S + 15) / 16 * 16;
     const int smem = 4 * nkb * kTileBytes + 2 * 3 * nkb * kBlk * 4 + 2 * (*colsP) * ((*colsP) * 2 + 16);

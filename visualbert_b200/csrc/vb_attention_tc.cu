@@ -1,31 +1,37 @@
-// vb_attention_tc.cu — attention forward on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), seq <= 256.
+// vb_attention_tc.cu — attention forward on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), seq <= 192.
 //
-// One persistent CTA per SM walks over work items (batch b, head h, 128-query tile qt):
-//   warp 0      TMA producer: Q tile [128 x 64], K [Npad x 64], V [Npad x 64] of the head (3-D tensor map over
-//               qkv[B][S][3H], so rows >= S are zero-filled), 2-stage mbarrier ring
-//   warp 1      MMA issuer:   S = Q K^T   tcgen05.mma 128 x Npad x 16, 4 k-steps, accumulator in TMEM (double-buffered,
-//                                          so QK^T of item i+1 runs under the softmax of item i)
-//                             O = P V     tcgen05.mma 128 x 64 x 16, Npad/16 k-steps, P read from shared memory
-//                                          (K-major, 128B-swizzled A tile written by the softmax warps), V MN-major
-//   warp 2      TMEM allocator
-//   warps 4-19  softmax + epilogue, 4 warp-groups: row r of the tile is TMEM lane r, and its key range is split
-//               over 4 threads (warp-group g owns the 16-column chunks c = g, g+4, ...), so every SM sub-partition
-//               has 4 softmax warps to hide ALU/SFU/TMEM latency. Row max and exp2 straight from TMEM (two passes,
-//               no online rescaling because the whole key range is in TMEM; partial max / sum exchanged through
-//               shared memory), attention dropout (keep-mask drawn here and stored packed for the backward),
-//               P -> bf16 -> swizzled smem tile, then O * 1/l -> bf16 -> 32-byte stores, LSE for the backward.
+// Same math as reference modeling.py:241-256 (scale, additive mask, softmax, dropout on the probabilities, P V, head
+// merge). One persistent CTA per SM walks over (batch, head) items; an item is nq <= 2 query tiles of 128 rows.
 //
-// Same math as reference modeling.py:241-256 (scale, additive mask, softmax, dropout, P V, head merge).
+//   warp 0       TMA producer: Q tile(s), K [npad x 64], V [npad x 64] of the head through 3-D tensor maps over
+//                qkv[B][S][3H] (rows >= S arrive as zeros), 2-stage mbarrier ring, one stage per item
+//   warp 1       MMA issuer (one thread):
+//                  S = Q K^T   tcgen05.mma 128 x npad x 16, 4 k-steps, fp32 accumulator in TMEM (two S buffers)
+//                  O = P V     tcgen05.mma 128 x 64 x 16, npad/16 k-steps, A = P read FROM TMEM (bf16, written in place over
+//                              the consumed scores by the softmax threads: no shared-memory round trip), B = V (MN-major)
+//   warp 2       TMEM allocator (512 columns: S0 | S1 | O0 | O1)
+//   warp 3       stages the item's additive key-mask row (x log2 e) in shared memory
+//   warps 4-7    softmax warp-group 0, warps 8-11 softmax warp-group 1: tile n of the CTA's tile sequence belongs to
+//                group n % 2 and to TMEM buffers n % 2, so the QK^T of tile n+2 and the P V of tile n+1 run under the
+//                softmax of the other group. One thread per query row (row == TMEM lane): two passes over the row
+//                straight out of TMEM (max, then exp2 / sum / dropout / bf16 -> TMEM), no cross-thread exchange.
+//
+// Lane balance for seq = 128 + r (the benchmark's 164 = 128 + 36): the short second tile would keep only lane
+// quarter 0 (and a sliver of quarter 1) busy, i.e. always the same SM sub-partition. Its rows are therefore placed at a
+// ROTATING row offset inside the 128-row MMA tile (0, 32, 64, 88 for successive items): the Q rows are TMA-loaded into a
+// compact window and the UMMA descriptor simply starts `offset` rows earlier (the rows outside the window are whatever
+// shared memory holds — rows of S/O are independent, the garbage rows are never read back).
 #include "vb_attention.cuh"
 
 namespace vb {
 
 namespace {
 
-constexpr int kQRows = 128;            // query rows per work item (UMMA M)
-constexpr int kSoftmaxWgs = 4;          // softmax warp-groups: each row's key range is split over 4 threads
-constexpr int kSoftmaxThreads = 128 * kSoftmaxWgs;
-constexpr int kThreadsTc = 128 + kSoftmaxThreads;
+constexpr int kQRows = 128;           // query rows per tile (UMMA M)
+constexpr int kWgThreads = 128;       // one softmax warp-group
+constexpr int kThreadsTc = 128 + 2 * kWgThreads;
+constexpr int kMaxNpad = 192;         // two S buffers of <= 192 columns + two O buffers of 64 = 512 TMEM columns
+constexpr int kStagesTc = 2;
 
 __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
     asm volatile(
@@ -50,27 +56,26 @@ __device__ __forceinline__ uint32_t idesc_bf16(int m, int n, bool a_mn, bool b_m
            (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-struct TcLayout {  // shared-memory carve-up (bytes), all tile bases 1 KB aligned
-    int kv_bytes;      // Npad * 128 rounded up to 1 KB
-    int stage_bytes;   // Q + K + V
-    int nstage;
-    int p_off, p_bytes;
-    int bias_off;      // fp32 [2][256]
-    int xchg_off;
+struct TcLayout {  // shared-memory carve-up (bytes from the 1 KB-aligned base)
+    int kv_bytes;     // npad * 128 rounded up to 1 KB
+    int stage_bytes;  // Q1 + K + V
+    int q2_bytes;     // compact window of the second query tile (0 when nq == 1)
+    int q2_off;       // the two windows sit BETWEEN the two stages: >= 16 KB of valid shared memory on both sides
+    int stage1_off;
+    int bias_off;     // fp32 [2][kMaxNpad]
     int bar_off;
     int tmem_ptr_off;
     int total;
 };
-__host__ __device__ inline TcLayout tc_layout(int npad, int nstage) {
+__host__ __device__ inline TcLayout tc_layout(int npad, int r2pad) {
     TcLayout L;
     L.kv_bytes = ((npad * 128 + 1023) / 1024) * 1024;
     L.stage_bytes = kQRows * 128 + 2 * L.kv_bytes;
-    L.nstage = nstage;
-    L.p_off = nstage * L.stage_bytes;
-    L.p_bytes = ((npad + 63) / 64) * kQRows * 128;
-    L.bias_off = L.p_off + L.p_bytes;
-    L.xchg_off = L.bias_off + 2 * 256 * 4;                       // fp32 [2 parities][max|sum][4 wgs][128 rows]
-    L.bar_off = L.xchg_off + 2 * 2 * kSoftmaxWgs * 128 * 4;
+    L.q2_bytes = ((r2pad * 128 + 1023) / 1024) * 1024;
+    L.q2_off = L.stage_bytes;
+    L.stage1_off = L.q2_off + 2 * L.q2_bytes;
+    L.bias_off = L.stage1_off + L.stage_bytes;
+    L.bar_off = L.bias_off + 2 * kMaxNpad * 4;
     L.tmem_ptr_off = L.bar_off + 16 * 8;
     L.total = L.tmem_ptr_off + 16 + 1024;
     return L;
@@ -78,48 +83,57 @@ __host__ __device__ inline TcLayout tc_layout(int npad, int nstage) {
 
 struct TcParams {
     AttnParams a;
-    int npad;      // keys padded to a multiple of 16
-    int nq;        // query tiles per head
-    int nkb;       // ceil(S / 64)
-    int nstage;    // input stages (2 if they fit)
-    int nsbuf;     // TMEM score buffers (2 if they fit)
-    long long* dbg; // optional: clock64 stamps of CTA 0 (VB_TC_DEBUG=1), [16 items][8 stamps]
+    int npad;    // keys padded to a multiple of 16
+    int nq;      // query tiles per item (1 or 2)
+    int r2;      // rows of the second tile (S - 128), 0 when nq == 1
+    int r2pad;   // r2 rounded up to 8
+    int nkb;     // ceil(S / 64): 64-bit keep words per query row
+    long long* dbg;  // optional clock64 stamps of CTA 0 (VB_TC_DEBUG=1): [tile < 32][16]
 };
 
+// row offset of the second tile's window inside its 128-row MMA tile for the li-th item of this CTA
+__device__ __forceinline__ int tile2_offset(int li, int r2pad) {
+    const int lim = kQRows - r2pad;  // multiple of 8
+    const int o = (li & 3) * 32;
+    return o < lim ? o : lim;
+}
+
 __global__ void __launch_bounds__(kThreadsTc, 1)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const TcParams tp) {
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQ2,
+                   const __grid_constant__ CUtensorMap tmKV, const TcParams tp) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - raw);
     const AttnParams& p = tp.a;
-    const TcLayout L = tc_layout(tp.npad, tp.nstage);
+    const TcLayout L = tc_layout(tp.npad, tp.r2pad);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int S = p.S, npad = tp.npad;
+    const int S = p.S, npad = tp.npad, nq = tp.nq;
 
-    auto q_tile = [&](int s) { return base + s * L.stage_bytes; };
-    auto k_tile = [&](int s) { return base + s * L.stage_bytes + kQRows * 128; };
-    auto v_tile = [&](int s) { return base + s * L.stage_bytes + kQRows * 128 + L.kv_bytes; };
-    const uint32_t p_tile = base + L.p_off;
+    auto stage_base = [&](int s) { return base + (s ? L.stage1_off : 0); };
+    auto q_tile = [&](int s) { return stage_base(s); };
+    auto k_tile = [&](int s) { return stage_base(s) + kQRows * 128; };
+    auto v_tile = [&](int s) { return stage_base(s) + kQRows * 128 + L.kv_bytes; };
+    auto q2_win = [&](int s) { return base + L.q2_off + s * L.q2_bytes; };
     auto bar = [&](int i) { return base + L.bar_off + 8 * i; };
-    // barrier indices
-    enum { FULL0 = 0, EMPTY0 = 2, SFULL0 = 4, SEMPTY0 = 6, PFULL = 8, OFULL = 9, OEMPTY = 10 };
+    enum { FULL0 = 0, EMPTY0 = 2, SFULL0 = 4, PFULL0 = 6, OFULL0 = 8, OEMPTY0 = 10 };
     volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + L.tmem_ptr_off);
+    float* sbias_all = reinterpret_cast<float*>(smem + L.bias_off);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmQ2);
         tma_prefetch_desc(&tmKV);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(bar(FULL0 + s), 1);
-            mbar_init(bar(EMPTY0 + s), 1);
+            mbar_init(bar(FULL0 + s), 2);             // TMA producer (expect_tx) + the mask-row stager
+            mbar_init(bar(EMPTY0 + s), 1);            // tcgen05.commit after the item's last MMA
             mbar_init(bar(SFULL0 + s), 1);
-            mbar_init(bar(SEMPTY0 + s), kSoftmaxThreads);
+            mbar_init(bar(PFULL0 + s), kWgThreads);
+            mbar_init(bar(OFULL0 + s), 1);
+            mbar_init(bar(OEMPTY0 + s), kWgThreads);
         }
-        mbar_init(bar(PFULL), kSoftmaxThreads);
-        mbar_init(bar(OFULL), 1);
-        mbar_init(bar(OEMPTY), kSoftmaxThreads);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(base + L.tmem_ptr_off, 512);
@@ -127,31 +141,27 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    const uint32_t tmem_o = tmem_base + 448;                              // O accumulator: columns 448..511
-    auto tmem_s = [&](int sb) { return tmem_base + (sb ? 224u : 0u); };   // score buffers at 0 and 224
+    auto tmem_s = [&](int b) { return tmem_base + static_cast<uint32_t>(b * kMaxNpad); };
+    auto tmem_o = [&](int b) { return tmem_base + static_cast<uint32_t>(2 * kMaxNpad + b * kHd); };
+    pdl_trigger();
+    pdl_wait();
 
-    const int total = p.B * p.A * tp.nq;
+    const int total = p.B * p.A;
     const int n_local = (total - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-    auto decode = [&](int li, int& b, int& h, int& qt) {
-        const int item = blockIdx.x + li * gridDim.x;
-        qt = item % tp.nq;
-        const int bh = item / tp.nq;
-        h = bh % p.A;
-        b = bh / p.A;
-    };
-    const uint32_t stage_tx = static_cast<uint32_t>(kQRows * 128 + 2 * npad * 128);
+    const int n_tiles = n_local * nq;
 
     if (warp == 0) {
         if (lane == 0) {
             // ---------------- TMA producer ----------------
+            const uint32_t stage_tx = static_cast<uint32_t>(kQRows * 128 + 2 * npad * 128 + (nq == 2 ? tp.r2pad * 128 : 0));
             for (int li = 0; li < n_local; ++li) {
-                int b, h, qt;
-                decode(li, b, h, qt);
-                const int s = li % tp.nstage;
-                const uint32_t ph = (li / tp.nstage) & 1;
-                mbar_wait(bar(EMPTY0 + s), ph ^ 1u);
+                const int item = blockIdx.x + li * gridDim.x;
+                const int b = item / p.A, h = item % p.A;
+                const int s = li % kStagesTc;
+                mbar_wait(bar(EMPTY0 + s), ((li / kStagesTc) & 1) ^ 1u);
                 mbar_arrive_expect_tx(bar(FULL0 + s), stage_tx);
-                tma_load_3d(q_tile(s), &tmQ, bar(FULL0 + s), h * kHd, qt * kQRows, b);
+                tma_load_3d(q_tile(s), &tmQ, bar(FULL0 + s), h * kHd, 0, b);
+                if (nq == 2) tma_load_3d(q2_win(s), &tmQ2, bar(FULL0 + s), h * kHd, kQRows, b);
                 tma_load_3d(k_tile(s), &tmKV, bar(FULL0 + s), p.H + h * kHd, 0, b);
                 tma_load_3d(v_tile(s), &tmKV, bar(FULL0 + s), 2 * p.H + h * kHd, 0, b);
             }
@@ -161,190 +171,211 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             // ---------------- MMA issuer ----------------
             const uint32_t idesc_qk = idesc_bf16(kQRows, npad, false, false);
             const uint32_t idesc_pv = idesc_bf16(kQRows, kHd, false, true);
-            auto do_qk = [&](int j) {
-                const int s = j % tp.nstage, sb = j % tp.nsbuf;
-                mbar_wait(bar(FULL0 + s), (j / tp.nstage) & 1);
-                mbar_wait(bar(SEMPTY0 + sb), ((j / tp.nsbuf) & 1) ^ 1u);
+            auto issue_s = [&](int n) {
+                const int li = n / nq, t = n - li * nq;
+                const int s = li % kStagesTc, bf = n & 1;
+                mbar_wait(bar(FULL0 + s), (li / kStagesTc) & 1);
                 tcgen05_fence_after();
+                // tile 0: the 128-row Q tile; tile 1: the compact window, addressed `offset` rows before its start
+                const uint32_t qa = t == 0 ? q_tile(s) : q2_win(s) - static_cast<uint32_t>(tile2_offset(li, tp.r2pad) * 128);
 #pragma unroll
                 for (int k = 0; k < kHd / 16; ++k) {
-                    const uint64_t ad = smem_desc_sw128(q_tile(s) + k * 32, 0, 1024);
+                    const uint64_t ad = smem_desc_sw128(qa + k * 32, 0, 1024);
                     const uint64_t bd = smem_desc_sw128(k_tile(s) + k * 32, 0, 1024);
-                    umma_bf16(tmem_s(sb), ad, bd, idesc_qk, k > 0 ? 1u : 0u);
+                    umma_bf16(tmem_s(bf), ad, bd, idesc_qk, k > 0 ? 1u : 0u);
                 }
-                umma_commit(bar(SFULL0 + sb));
+                umma_commit(bar(SFULL0 + bf));
+                if (tp.dbg != nullptr && blockIdx.x == 0 && n < 32) tp.dbg[n * 16 + 12] = clock64();
             };
-            if (n_local > 0) do_qk(0);
-            for (int li = 0; li < n_local; ++li) {
-                if (li + 1 < n_local && tp.nsbuf == 2 && tp.nstage == 2) do_qk(li + 1);  // under the softmax of item li
-                const int s = li % tp.nstage;
-                mbar_wait(bar(PFULL), li & 1);
-                mbar_wait(bar(OEMPTY), (li & 1) ^ 1u);
+            auto issue_pv = [&](int n) {
+                const int li = n / nq, t = n - li * nq;
+                const int s = li % kStagesTc, bf = n & 1;
+                const uint32_t ph = (n >> 1) & 1;
+                const bool stamp = tp.dbg != nullptr && blockIdx.x == 0 && n < 32;
+                if (stamp) tp.dbg[n * 16 + 8] = clock64();
+                mbar_wait(bar(PFULL0 + bf), ph);
+                if (stamp) tp.dbg[n * 16 + 9] = clock64();
+                mbar_wait(bar(OEMPTY0 + bf), ph ^ 1u);
                 tcgen05_fence_after();
+                if (stamp) tp.dbg[n * 16 + 10] = clock64();
                 const int ksteps = npad / 16;
                 for (int k = 0; k < ksteps; ++k) {
-                    // P: K-major A, 64-key atoms of [128 rows x 128 B]; V: MN-major B, [keys x 128 B], 16 key rows per step
-                    const uint64_t ad = smem_desc_sw128(p_tile + (k >> 2) * (kQRows * 128) + (k & 3) * 32, 0, 1024);
+                    // A = P: bf16 in TMEM, 16 keys = 8 columns; B = V: MN-major [keys x 128 B], 16 key rows per step
                     const uint64_t bd = smem_desc_sw128(v_tile(s) + k * 2048, 0, 1024);
-                    umma_bf16(tmem_o, ad, bd, idesc_pv, k > 0 ? 1u : 0u);
+                    umma_bf16_ts(tmem_o(bf), tmem_s(bf) + k * 8, bd, idesc_pv, k > 0 ? 1u : 0u);
                 }
-                umma_commit(bar(OFULL));
-                umma_commit(bar(EMPTY0 + s));
-                if (li + 1 < n_local && !(tp.nsbuf == 2 && tp.nstage == 2)) do_qk(li + 1);
+                umma_commit(bar(OFULL0 + bf));
+                if (t == nq - 1) umma_commit(bar(EMPTY0 + s));  // every MMA of the item has retired: Q / K / V are free
+                if (stamp) tp.dbg[n * 16 + 11] = clock64();
+            };
+            if (n_tiles > 0) issue_s(0);
+            if (n_tiles > 1) issue_s(1);
+            for (int n = 0; n < n_tiles; ++n) {
+                issue_pv(n);
+                // S(n+2) reuses the TMEM buffer P(n) lives in: the tensor pipe executes MMAs in issue order
+                if (n + 2 < n_tiles) issue_s(n + 2);
             }
         }
+    } else if (warp == 3) {
+        // ---------------- additive key-mask row of the item, log2 domain; -inf on the padding keys ----------------
+        for (int li = 0; li < n_local; ++li) {
+            const int item = blockIdx.x + li * gridDim.x;
+            const int b = item / p.A;
+            const int s = li % kStagesTc;
+            mbar_wait(bar(EMPTY0 + s), ((li / kStagesTc) & 1) ^ 1u);
+            float* sb = sbias_all + s * kMaxNpad;
+            for (int i = lane; i < npad; i += 32)
+                sb[i] = i < S ? __ldg(p.mask_bias + static_cast<long long>(b) * S + i) * kLog2e : -INFINITY;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(FULL0 + s));
+        }
     } else if (warp >= 4) {
-        // ---------------- softmax + epilogue: 4 threads per query row ----------------
+        // ---------------- softmax + epilogue: one thread per query row ----------------
+        const int g = (warp - 4) >> 2;           // warp-group = TMEM buffer
         const int q4 = warp & 3;                 // TMEM lane quarter of this warp
-        const int wg = (warp - 4) >> 2;          // warp-group 0..3 = column phase
-        const int r = q4 * 32 + lane;            // row inside the 128-row tile == TMEM lane
-        const int st = threadIdx.x - 128;        // 0..511
+        const int r = q4 * 32 + lane;            // row inside the tile == TMEM lane
         const uint32_t lane_sel = static_cast<uint32_t>(q4 * 32) << 16;
-        float* sbias_all = reinterpret_cast<float*>(smem + L.bias_off);
-        float* xchg_all = reinterpret_cast<float*>(smem + L.xchg_off);
         const float sc2 = p.scale * kLog2e;
         const int nchunk = npad / 16;
-        auto stage_bias = [&](int li) {
-            int b, h, qt;
-            decode(li, b, h, qt);
-            float* sb = sbias_all + (li & 1) * 256;
-            for (int i = st; i < npad; i += kSoftmaxThreads)
-                sb[i] = i < S ? p.mask_bias[static_cast<long long>(b) * S + i] * kLog2e : -INFINITY;
-        };
-        if (n_local > 0) stage_bias(0);
-        named_bar_sync(2, kSoftmaxThreads);
-        for (int li = 0; li < n_local; ++li) {
-            int b, h, qt;
-            decode(li, b, h, qt);
-            const int sb = li % tp.nsbuf;
-            const unsigned bh = static_cast<unsigned>(b * p.A + h);
-            const float* sbias = sbias_all + (li & 1) * 256;
-            float* xmax = xchg_all + (li & 1) * (2 * kSoftmaxWgs * 128);
-            float* xsum = xmax + kSoftmaxWgs * 128;
-            const bool stamp = tp.dbg != nullptr && blockIdx.x == 0 && st == 0 && li < 16;
-            if (stamp) tp.dbg[li * 8 + 0] = clock64();
-            if (li + 1 < n_local) stage_bias(li + 1);   // visible to everyone after this item's named barrier
-            mbar_wait(bar(SFULL0 + sb), (li / tp.nsbuf) & 1);
+        const bool drop = p.drop_scale != 0.f;
+        const int np64 = tp.nkb * kBlk;
+        for (int n = g; n < n_tiles; n += 2) {
+            const int li = n / nq, t = n - li * nq;
+            const int item = blockIdx.x + li * gridDim.x;
+            const int b = item / p.A, h = item % p.A;
+            const int s = li % kStagesTc;
+            const uint32_t ph = (n >> 1) & 1;
+            int q;
+            bool valid;
+            if (t == 0) {
+                q = r;
+                valid = r < S;
+            } else {
+                const int off = tile2_offset(li, tp.r2pad);
+                q = kQRows + r - off;
+                valid = r >= off && r < off + tp.r2;
+            }
+            const bool wvalid = __any_sync(0xffffffffu, valid);
+            // keep words of this query row (drawn by attn_keep_mask_kernel): up to 3 x 64 keys
+            unsigned long long kw0 = ~0ull, kw1 = ~0ull, kw2 = ~0ull;
+            if (drop && valid) {
+                const unsigned long long* kp = p.keep + (static_cast<unsigned long long>(item) * np64 + q) * tp.nkb;
+                kw0 = kp[0];
+                if (tp.nkb > 1) kw1 = kp[1];
+                if (tp.nkb > 2) kw2 = kp[2];
+            }
+            const float* sbias = sbias_all + s * kMaxNpad;
+            const bool stamp = tp.dbg != nullptr && blockIdx.x == 0 && (threadIdx.x & 127) == 0 && n < 32;
+            if (stamp) tp.dbg[n * 16 + 0] = clock64();
+            mbar_wait(bar(FULL0 + s), (li / kStagesTc) & 1);   // mask row staged (and visible) for this item
+            mbar_wait(bar(SFULL0 + g), ph);
             tcgen05_fence_after();
-            if (stamp) tp.dbg[li * 8 + 1] = clock64();
-            const uint32_t ts = tmem_s(sb) + lane_sel;
-            const int q = qt * kQRows + r;       // query index inside the head
-            // Each thread streams ITS chunks (c = wg, wg+4, ...) out of TMEM with the next chunk's tcgen05.ld in flight.
-            // ---- pass 1: partial row maximum of the scaled, masked scores ----
-            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-            auto pass1 = [&](const uint32_t (&v)[16], int c) {
-                const float4* b4 = reinterpret_cast<const float4*>(sbias + c * 16);
+            if (stamp) tp.dbg[n * 16 + 1] = clock64();
+            const uint32_t ts = tmem_s(g) + lane_sel;
+            float m = 0.f, lsum = 1.f;
+            if (wvalid) {
+                // ---- pass 1: row maximum of the scaled, masked scores (next chunk's tcgen05.ld in flight) ----
+                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+                auto pass1 = [&](const uint32_t (&v)[16], int c) {
+                    const float4* b4 = reinterpret_cast<const float4*>(sbias + c * 16);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 bb = b4[j];
+                        mx0 = fmaxf(mx0, fmaf(__uint_as_float(v[4 * j]), sc2, bb.x));
+                        mx1 = fmaxf(mx1, fmaf(__uint_as_float(v[4 * j + 1]), sc2, bb.y));
+                        mx2 = fmaxf(mx2, fmaf(__uint_as_float(v[4 * j + 2]), sc2, bb.z));
+                        mx3 = fmaxf(mx3, fmaf(__uint_as_float(v[4 * j + 3]), sc2, bb.w));
+                    }
+                };
+                {
+                    uint32_t va[16], vb_[16];
+                    tmem_ld_32x32b_x16(ts, va);
+                    for (int c = 0; c < nchunk; c += 2) {
+                        tmem_ld_wait();
+                        if (c + 1 < nchunk) tmem_ld_32x32b_x16(ts + (c + 1) * 16, vb_);
+                        pass1(va, c);
+                        if (c + 1 < nchunk) {
+                            tmem_ld_wait();
+                            if (c + 2 < nchunk) tmem_ld_32x32b_x16(ts + (c + 2) * 16, va);
+                            pass1(vb_, c + 1);
+                        }
+                    }
+                }
+                m = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                if (stamp) tp.dbg[n * 16 + 2] = clock64();
+                // ---- pass 2: probabilities, row sum, dropout, bf16 P written over the consumed scores in TMEM ----
+                float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
+                auto pass2 = [&](const uint32_t (&v)[16], int c) {
+                    const float4* b4 = reinterpret_cast<const float4*>(sbias + c * 16);
+                    float pr[16];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 bb = b4[j];
+                        pr[4 * j] = fast_ex2(fmaf(__uint_as_float(v[4 * j]), sc2, bb.x) - m);
+                        pr[4 * j + 1] = fast_ex2(fmaf(__uint_as_float(v[4 * j + 1]), sc2, bb.y) - m);
+                        pr[4 * j + 2] = fast_ex2(fmaf(__uint_as_float(v[4 * j + 2]), sc2, bb.z) - m);
+                        pr[4 * j + 3] = fast_ex2(fmaf(__uint_as_float(v[4 * j + 3]), sc2, bb.w) - m);
+                        ls0 += pr[4 * j]; ls1 += pr[4 * j + 1]; ls2 += pr[4 * j + 2]; ls3 += pr[4 * j + 3];
+                    }
+                    if (drop) {
+                        // chunk c = keys 16c .. 16c+15 = the 16-bit slice (c & 3) of keep word (c >> 2).
+                        // The 1/(1-p) factor is folded into the final 1/l normalisation of the output row.
+                        const unsigned long long w = c < 4 ? kw0 : (c < 8 ? kw1 : kw2);
+                        const uint32_t bits = static_cast<uint32_t>(w >> ((c & 3) * 16));
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) pr[i] = ((bits >> i) & 1u) ? pr[i] : 0.f;
+                    }
+                    uint32_t w8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) w8[i] = pack_bf16x2(pr[2 * i], pr[2 * i + 1]);
+                    tmem_st_32x32b_x8(ts + c * 8, w8);   // columns 8c .. 8c+7 lie inside chunks <= c: already consumed
+                };
+                {
+                    uint32_t va[16], vb_[16];
+                    tmem_ld_32x32b_x16(ts, va);
+                    for (int c = 0; c < nchunk; c += 2) {
+                        tmem_ld_wait();
+                        if (c + 1 < nchunk) tmem_ld_32x32b_x16(ts + (c + 1) * 16, vb_);
+                        pass2(va, c);
+                        if (c + 1 < nchunk) {
+                            tmem_ld_wait();
+                            if (c + 2 < nchunk) tmem_ld_32x32b_x16(ts + (c + 2) * 16, va);
+                            pass2(vb_, c + 1);
+                        }
+                    }
+                }
+                lsum = (ls0 + ls1) + (ls2 + ls3);
+                tmem_st_wait();
+            }
+            tcgen05_fence_before();
+            mbar_arrive(bar(PFULL0 + g));
+            if (stamp) tp.dbg[n * 16 + 3] = clock64();
+            // ---- epilogue: O row * (dropout scale / l) -> bf16 -> four 32-byte stores ----
+            mbar_wait(bar(OFULL0 + g), ph);
+            tcgen05_fence_after();
+            if (stamp) tp.dbg[n * 16 + 4] = clock64();
+            uint32_t o[4][16];
+            if (wvalid) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) tmem_ld_32x32b_x16(tmem_o(g) + lane_sel + j * 16, o[j]);
+                tmem_ld_wait();
+            }
+            tcgen05_fence_before();
+            mbar_arrive(bar(OEMPTY0 + g));
+            if (valid) {
+                const float inv = (drop ? p.drop_scale : 1.f) / lsum;
+                bf16* dst = p.ctx + (static_cast<long long>(b) * S + q) * p.H + h * kHd;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float4 bb = b4[j];
-                    mx[0] = fmaxf(mx[0], fmaf(__uint_as_float(v[4 * j]), sc2, bb.x));
-                    mx[1] = fmaxf(mx[1], fmaf(__uint_as_float(v[4 * j + 1]), sc2, bb.y));
-                    mx[2] = fmaxf(mx[2], fmaf(__uint_as_float(v[4 * j + 2]), sc2, bb.z));
-                    mx[3] = fmaxf(mx[3], fmaf(__uint_as_float(v[4 * j + 3]), sc2, bb.w));
+                    uint32_t w[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        w[i] = pack_bf16x2(__uint_as_float(o[j][2 * i]) * inv, __uint_as_float(o[j][2 * i + 1]) * inv);
+                    stg_v8(dst + j * 16, w);
                 }
-            };
-            {
-                uint32_t va[16], vb_[16];
-                if (wg < nchunk) tmem_ld_32x32b_x16(ts + wg * 16, va);
-                for (int c = wg; c < nchunk; c += 2 * kSoftmaxWgs) {
-                    tmem_ld_wait();
-                    if (c + kSoftmaxWgs < nchunk) tmem_ld_32x32b_x16(ts + (c + kSoftmaxWgs) * 16, vb_);
-                    pass1(va, c);
-                    if (c + kSoftmaxWgs < nchunk) {
-                        tmem_ld_wait();
-                        if (c + 2 * kSoftmaxWgs < nchunk) tmem_ld_32x32b_x16(ts + (c + 2 * kSoftmaxWgs) * 16, va);
-                        pass1(vb_, c + kSoftmaxWgs);
-                    }
-                }
+                if (p.lse != nullptr) p.lse[static_cast<long long>(item) * S + q] = (m + log2f(lsum)) * 0.6931471805599453f;
             }
-            xmax[wg * 128 + r] = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-            if (stamp) tp.dbg[li * 8 + 2] = clock64();
-            named_bar_sync(2, kSoftmaxThreads);
-            if (stamp) tp.dbg[li * 8 + 3] = clock64();
-            const float m = fmaxf(fmaxf(xmax[r], xmax[128 + r]), fmaxf(xmax[256 + r], xmax[384 + r]));
-            // ---- pass 2: probabilities, partial row sum, dropout, bf16 P tile in shared memory ----
-            float ls[4] = {0.f, 0.f, 0.f, 0.f};
-            auto pass2 = [&](const uint32_t (&v)[16], int c) {
-                const float4* b4 = reinterpret_cast<const float4*>(sbias + c * 16);
-                float pr[16];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 bb = b4[j];
-                    pr[4 * j] = fast_ex2(fmaf(__uint_as_float(v[4 * j]), sc2, bb.x) - m);
-                    pr[4 * j + 1] = fast_ex2(fmaf(__uint_as_float(v[4 * j + 1]), sc2, bb.y) - m);
-                    pr[4 * j + 2] = fast_ex2(fmaf(__uint_as_float(v[4 * j + 2]), sc2, bb.z) - m);
-                    pr[4 * j + 3] = fast_ex2(fmaf(__uint_as_float(v[4 * j + 3]), sc2, bb.w) - m);
-                    ls[0] += pr[4 * j]; ls[1] += pr[4 * j + 1]; ls[2] += pr[4 * j + 2]; ls[3] += pr[4 * j + 3];
-                }
-                if (p.drop_scale != 0.f) {
-                    uint32_t bits = 0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {  // one hash -> 4 x 8 random bits -> 4 keys
-                        const uint32_t hsh = mix32(((((bh * static_cast<unsigned>(S) + static_cast<unsigned>(q)) << 6) + c * 4 + j)) ^ p.drop_seed);
-                        bits |= static_cast<uint32_t>((hsh & 0xffu) >= p.drop_thresh16) << (4 * j);
-                        bits |= static_cast<uint32_t>(((hsh >> 8) & 0xffu) >= p.drop_thresh16) << (4 * j + 1);
-                        bits |= static_cast<uint32_t>(((hsh >> 16) & 0xffu) >= p.drop_thresh16) << (4 * j + 2);
-                        bits |= static_cast<uint32_t>((hsh >> 24) >= p.drop_thresh16) << (4 * j + 3);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) pr[i] = ((bits >> i) & 1u) ? pr[i] * p.drop_scale : 0.f;
-                    // chunk c = 16 keys = the 16-bit slice (c & 3) of the 64-bit keep word (c >> 2) of this query row
-                    if (q < tp.nkb * kBlk)
-                        reinterpret_cast<unsigned short*>(p.keep)[((static_cast<unsigned long long>(bh) * (tp.nkb * kBlk) + q) * tp.nkb + (c >> 2)) * 4 + (c & 3)] =
-                            static_cast<unsigned short>(bits);
-                }
-                // 16 keys = two 16-byte chunks of row r in the 64-key atom (c / 4)
-                const uint32_t atom = p_tile + (c >> 2) * (kQRows * 128) + r * 128;
-                const int ch0 = (c & 3) * 2;
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(atom + ((ch0 ^ (r & 7)) << 4)),
-                             "r"(pack_bf16x2(pr[0], pr[1])), "r"(pack_bf16x2(pr[2], pr[3])), "r"(pack_bf16x2(pr[4], pr[5])),
-                             "r"(pack_bf16x2(pr[6], pr[7])) : "memory");
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(atom + (((ch0 + 1) ^ (r & 7)) << 4)),
-                             "r"(pack_bf16x2(pr[8], pr[9])), "r"(pack_bf16x2(pr[10], pr[11])), "r"(pack_bf16x2(pr[12], pr[13])),
-                             "r"(pack_bf16x2(pr[14], pr[15])) : "memory");
-            };
-            {
-                uint32_t va[16], vb_[16];
-                if (wg < nchunk) tmem_ld_32x32b_x16(ts + wg * 16, va);
-                for (int c = wg; c < nchunk; c += 2 * kSoftmaxWgs) {
-                    tmem_ld_wait();
-                    if (c + kSoftmaxWgs < nchunk) tmem_ld_32x32b_x16(ts + (c + kSoftmaxWgs) * 16, vb_);
-                    pass2(va, c);
-                    if (c + kSoftmaxWgs < nchunk) {
-                        tmem_ld_wait();
-                        if (c + 2 * kSoftmaxWgs < nchunk) tmem_ld_32x32b_x16(ts + (c + 2 * kSoftmaxWgs) * 16, va);
-                        pass2(vb_, c + kSoftmaxWgs);
-                    }
-                }
-            }
-            xsum[wg * 128 + r] = (ls[0] + ls[1]) + (ls[2] + ls[3]);  // read after OFULL (ordered by the mbarrier chain)
-            if (stamp) tp.dbg[li * 8 + 4] = clock64();
-            tcgen05_fence_before();
-            mbar_arrive(bar(SEMPTY0 + sb));     // scores consumed: the next QK^T may overwrite this TMEM buffer
-            fence_proxy_async_smem();            // P (generic-proxy stores) -> visible to the tensor core (async proxy)
-            mbar_arrive(bar(PFULL));
-            // epilogue: warp-group g owns O columns 16g .. 16g+15 of its row
-            mbar_wait(bar(OFULL), li & 1);
-            tcgen05_fence_after();
-            if (stamp) tp.dbg[li * 8 + 5] = clock64();
-            uint32_t o[16];
-            tmem_ld_32x32b_x16(tmem_o + lane_sel + wg * 16, o);
-            tmem_ld_wait();
-            tcgen05_fence_before();
-            mbar_arrive(bar(OEMPTY));
-            if (q < S) {
-                const float lsum = (xsum[r] + xsum[128 + r]) + (xsum[256 + r] + xsum[384 + r]);
-                const float inv = 1.f / lsum;
-                bf16* dst = p.ctx + (static_cast<long long>(b) * S + q) * p.H + h * kHd + wg * 16;
-                uint32_t w[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    w[i] = pack_bf16x2(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
-                stg_v8(dst, w);
-                if (wg == 0 && p.lse != nullptr)
-                    p.lse[(static_cast<long long>(b) * p.A + h) * S + q] = (m + log2f(lsum)) * 0.6931471805599453f;
-            }
-            if (stamp) tp.dbg[li * 8 + 6] = clock64();
+            if (stamp) tp.dbg[n * 16 + 5] = clock64();
         }
     }
     tcgen05_fence_before();
@@ -359,7 +390,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_tmap_3d(CUtensorMap* m, const void* ptr, int S, int B, int ld, int box_rows) {
+}  // namespace
+
+// 3-D bf16 tensor map over x[B][S][ld]: box = 64 columns x box_rows rows x 1 batch, 128-byte swizzle, OOB rows -> 0
+int make_tmap_3d(CUtensorMap* m, const void* ptr, int S, int B, int ld, int box_rows) {
     static EncodeTiledFn fn = nullptr;
     if (fn == nullptr) {
         void* sym = nullptr;
@@ -380,52 +414,52 @@ static int make_tmap_3d(CUtensorMap* m, const void* ptr, int S, int B, int ld, i
     return 0;
 }
 
-}  // namespace
-
-bool attn_fwd_tc_supported(const AttnParams& p) { return p.S <= 256 && p.S >= 1 && (p.H * 3) % 8 == 0; }
+bool attn_fwd_tc_supported(const AttnParams& p) {
+    return p.S >= 1 && p.S <= kMaxNpad && (p.H * 3) % 8 == 0 && (reinterpret_cast<uintptr_t>(p.qkv) & 15) == 0;
+}
 
 int attn_fwd_tc(const AttnParams& p, cudaStream_t st) {
     TcParams tp;
     tp.a = p;
     tp.npad = ((p.S + 15) / 16) * 16;
-    tp.nq = (p.S + kQRows - 1) / kQRows;
+    tp.nq = p.S > kQRows ? 2 : 1;
+    tp.r2 = tp.nq == 2 ? p.S - kQRows : 0;
+    tp.r2pad = (tp.r2 + 7) / 8 * 8;
     tp.nkb = (p.S + kBlk - 1) / kBlk;
-    tp.nsbuf = tp.npad <= 224 ? 2 : 1;
-    tp.nstage = tc_layout(tp.npad, 2).total <= 227 * 1024 ? 2 : 1;
-    const TcLayout L = tc_layout(tp.npad, tp.nstage);
+    const TcLayout L = tc_layout(tp.npad, tp.r2pad);
     VB_REQUIRE(L.total <= 227 * 1024, "attention (tcgen05): shared memory %d bytes exceeds the limit", L.total);
-    CUtensorMap tq, tkv;
+    CUtensorMap tq, tq2, tkv;
     int rc = make_tmap_3d(&tq, p.qkv, p.S, p.B, 3 * p.H, kQRows);
+    if (rc) return rc;
+    rc = make_tmap_3d(&tq2, p.qkv, p.S, p.B, 3 * p.H, tp.nq == 2 ? tp.r2pad : 8);
     if (rc) return rc;
     rc = make_tmap_3d(&tkv, p.qkv, p.S, p.B, 3 * p.H, tp.npad);
     if (rc) return rc;
-    static int configured = 0;
-    if (configured < L.total) {
-        VB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-        configured = L.total;
-    }
-    const int total = p.B * p.A * tp.nq;
+    static int configured[kMaxDevices] = {0};
+    VB_CHECK_CUDA(ensure_dyn_smem(attn_fwd_tc_kernel, L.total, configured));
+    const int total = p.B * p.A;
     const int grid = total < num_sms() ? total : num_sms();
     static long long* dbg_buf = nullptr;
     static int dbg_calls = 0;
     const char* de = getenv("VB_TC_DEBUG");
     tp.dbg = nullptr;
     if (de != nullptr && atoi(de) != 0) {
-        if (dbg_buf == nullptr) cudaMallocManaged(&dbg_buf, 16 * 8 * sizeof(long long));
+        if (dbg_buf == nullptr) cudaMallocManaged(&dbg_buf, 32 * 16 * sizeof(long long));
         tp.dbg = dbg_buf;
     }
     {
         ProfScope ps(st, PROF_ATTN_FWD, 4.0 * p.B * p.A * p.S * p.S * kHd, 1);
-        attn_fwd_tc_kernel<<<grid, kThreadsTc, L.total, st>>>(tq, tkv, tp);
+        VB_CHECK_CUDA(launch_pdl(attn_fwd_tc_kernel, dim3(grid), dim3(kThreadsTc), static_cast<size_t>(L.total), st, tq, tq2, tkv, tp));
     }
     VB_CHECK_CUDA(cudaGetLastError());
     if (tp.dbg != nullptr && ++dbg_calls == 3) {  // third call: warm
         cudaStreamSynchronize(st);
-        printf("tc attention timeline (CTA 0, cycles): item: wait_S pass1 barrier pass2 wait_O epilogue | total\n");
-        for (int i = 0; i < 12; ++i) {
-            const long long* t = dbg_buf + i * 8;
-            printf("  item %2d: %6lld %6lld %6lld %6lld %6lld %6lld | %6lld\n", i, t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3],
-                   t[5] - t[4], t[6] - t[5], t[6] - t[0]);
+        const long long t0 = dbg_buf[0];
+        printf("tc attention timeline (CTA 0, cycles since first stamp)\n tile: start S_ready pass1 pass2/P_arrive O_ready end | mma: pv_enter P_ready O_empty pv_issued s_issued\n");
+        for (int i = 0; i < 16; ++i) {
+            const long long* t = dbg_buf + i * 16;
+            printf("  %2d: %7lld %7lld %7lld %7lld %7lld %7lld | %7lld %7lld %7lld %7lld %7lld\n", i, t[0] - t0, t[1] - t0, t[2] - t0, t[3] - t0,
+                   t[4] - t0, t[5] - t0, t[8] - t0, t[9] - t0, t[10] - t0, t[11] - t0, t[12] - t0);
         }
     }
     return 0;

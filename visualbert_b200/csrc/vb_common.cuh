@@ -18,7 +18,19 @@ typedef __nv_bfloat16 bf16;
 
 // host-side shared state / helpers (defined in vb_gemm.cu)
 extern std::atomic<long long> g_launches;  // kernel launches issued by this library
-int num_sms();
+int num_sms();      // SM count of the CALLER'S CURRENT device (cached per device)
+constexpr int kMaxDevices = 64;
+int current_device();  // cudaGetDevice, clamped to [0, kMaxDevices)
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: `cache` is the caller's static
+// per-device record of the size already configured (DataParallel threads / several devices in one process).
+template <typename K>
+inline cudaError_t ensure_dyn_smem(K kern, int bytes, int (&cache)[kMaxDevices]) {
+    const int d = current_device();
+    if (cache[d] >= bytes) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) cache[d] = bytes;
+    return e;
+}
 
 // Optional live profiling (vb_profile_enable): every launcher brackets its kernels with CUDA events on
 // the launch stream and tags them with a category and the algorithmic work (FLOPs or bytes) of the call.
@@ -367,6 +379,25 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)
           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr)
         : "memory");
+}
+// A operand from TMEM (TS form): D[tmem] (+)= A[tmem, K-major: lane = row, 2 bf16 per 32-bit column] * B[smem desc]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 8 columns of 32-bit: thread i of the warp writes row (lane base + i), 8 consecutive columns
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+                 "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

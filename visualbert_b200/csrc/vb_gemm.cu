@@ -673,26 +673,29 @@ int make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t out
     return 0;
 }
 
+int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev < 0 || dev >= kMaxDevices) ? 0 : dev;
+}
+
 int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
+    static int n[kMaxDevices] = {0};
+    const int dev = current_device();
+    if (n[dev] == 0) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        n[dev] = v > 0 ? v : 148;
     }
-    return n;
+    return n[dev];
 }
 
 template <bool A_MN, bool B_MN, int BLOCK_N, bool OUT_F32>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
     using C = Cfg<BLOCK_N>;
     auto kern = gemm_tcgen05_kernel<A_MN, B_MN, BLOCK_N, OUT_F32>;
-    static bool configured = false;
-    if (!configured) {
-        VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        configured = true;
-    }
+    static int configured[kMaxDevices] = {0};
+    VB_CHECK_CUDA(ensure_dyn_smem(kern, C::SMEM_BYTES, configured));
     const int m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
     const int n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
     const int tiles = m_blocks * n_blocks * p.splits;
@@ -708,11 +711,8 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
 template <bool A_MN, bool B_MN, bool OUT_F32>
 static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
     auto kern = gemm_tcgen05_2cta_kernel<A_MN, B_MN, OUT_F32>;
-    static bool configured = false;
-    if (!configured) {
-        VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES));
-        configured = true;
-    }
+    static int configured[kMaxDevices] = {0};
+    VB_CHECK_CUDA(ensure_dyn_smem(kern, Cfg2::SMEM_BYTES, configured));
     const int tiles = ((p.M + 255) / 256) * ((p.N + 255) / 256) * p.splits;
     int clusters = num_sms() / 2;
     if (clusters > tiles) clusters = tiles;

@@ -247,14 +247,11 @@ int ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, 
     const float scale = dq.scale, in_scale = iq.scale;
     const unsigned th = dq.thr8, in_th = iq.thr8;
     const size_t smem = static_cast<size_t>(2 * (H / 8) + kLnWarps * 6 * (H / 8)) * sizeof(float4);
-    static bool configured = false;
-    if (!configured) {
-        VB_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        VB_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        VB_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        VB_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        configured = true;
-    }
+    static int cfg1[kMaxDevices] = {0}, cfg2[kMaxDevices] = {0}, cfg3[kMaxDevices] = {0}, cfg4[kMaxDevices] = {0};
+    VB_CHECK_CUDA(ensure_dyn_smem(ln_bwd_kernel<1>, 100 * 1024, cfg1));
+    VB_CHECK_CUDA(ensure_dyn_smem(ln_bwd_kernel<2>, 100 * 1024, cfg2));
+    VB_CHECK_CUDA(ensure_dyn_smem(ln_bwd_kernel<3>, 100 * 1024, cfg3));
+    VB_CHECK_CUDA(ensure_dyn_smem(ln_bwd_kernel<4>, 100 * 1024, cfg4));
     ProfScope ps(st, PROF_LN_BWD, (dx_drop ? 8.0 : 6.0) * rows * H, 1);
 #define VB_LN_BWD(NC)                                                                                        \
     VB_CHECK_CUDA(launch_pdl(ln_bwd_kernel<NC>, dim3(grid), dim3(kLnWarps * 32), smem, st,                  \
