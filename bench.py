@@ -214,11 +214,13 @@ def run_ours(args):
     torch.cuda.synchronize()
     h2d_bytes = sum(v.numel() * v.element_size() for v in resident.values() if torch.is_tensor(v))
 
+    lscale = sync.loss_scale()   # 1 / world: the mean over ranks is folded into the loss, no divide pass over the buffer
+
     def step(batch):
         sync.zero()
         out = model(**batch)
-        out["loss"].backward()
-        sync.allreduce()
+        (out["loss"] * lscale if world > 1 else out["loss"]).backward()
+        sync.allreduce(prescaled=True)
         if opt is not None:
             opt.step()
         return out["loss"]

@@ -105,6 +105,21 @@ int vb_mask_bias(const int64_t* input_mask, const int64_t* image_mask, float* ou
                  int32_t num_regions, void* stream);
 int vb_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream); /* n % 8 == 0 */
 int vb_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream);
+/* Multi-tensor cast: one launch refreshes every bf16 compute copy (dst_fp32 = 0) and fp32 side copy (dst_fp32 = 1, e.g.
+ * the packed q|k|v bias) of a model from its fp32 master parameters. `table` lives in DEVICE memory, ordered by
+ * first_chunk; tensor i owns chunks [first_chunk, first_chunk + ceil(numel / VB_CAST_CHUNK)); n_chunks = their total.
+ * Replaces the implicit per-step .to(dtype) / fp16 master-copy handling around the reference forward
+ * (visualbert/models/train.py:122-136); called at the start of every training-mode forward so that ANY optimizer that
+ * changes the masters (the reference BertAdam updates through p.data, optimization.py:293) is seen. */
+#define VB_CAST_CHUNK 8192
+typedef struct {
+    const void* src;   /* fp32 master */
+    void* dst;         /* bf16 (or fp32) copy */
+    int64_t numel;
+    int32_t first_chunk;
+    int32_t dst_fp32;
+} vb_cast_item;        /* 32 bytes */
+int vb_cast_multi(const vb_cast_item* table, int32_t n_items, int32_t n_chunks, void* stream);
 int vb_colsum_bf16(const void* x, int64_t ld, float* out, int32_t rows, int32_t cols, void* stream); /* out += */
 
 /* ---- masked-LM loss (M.py:1471-1473, CrossEntropyLoss(ignore_index=-1) on the labelled rows) ------------- */

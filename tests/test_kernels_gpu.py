@@ -209,8 +209,13 @@ def test_attention_dropout_consistent_between_fwd_and_bwd():
     assert torch.equal(ctx, ctx2) and torch.equal(keep, keep2)
     # stored keep-mask: valid (query < S, key < S) bits are ~80 % ones for p = 0.2 (quantised to 51/256)
     nkb = (S + 63) // 64
-    words = keep.view(torch.int64).view(B * A, nkb * 64, nkb)[:, :S, :]
-    bits = ((words.unsqueeze(-1) >> torch.arange(64, device=dev)) & 1).reshape(B * A, S, nkb * 64)[:, :, :S]
+    both = keep.view(torch.int64).view(2, B * A, nkb * 64, nkb)   # [0]: rows = queries, [1]: the transpose (rows = keys)
+    unpack = lambda w: ((w.unsqueeze(-1) >> torch.arange(64, device=dev)) & 1).reshape(B * A, nkb * 64, nkb * 64)
+    bits, bits_t = unpack(both[0]), unpack(both[1])
+    import os
+    if os.environ.get("VB_ATTN_STAGED") != "1":  # the staged kernels (seq > 256) draw their own bits, query-major only
+        assert torch.equal(bits[:, :S, :S], bits_t[:, :S, :S].transpose(1, 2))
+    bits = bits[:, :S, :S]
     assert abs(bits.float().mean().item() - (1 - 51 / 256)) < 5e-3
     assert _rel(ctx, ref) > 0.05  # dropout really changed the output
     # O is linear in V: sum(dO * O) == sum(dV * V)

@@ -285,3 +285,42 @@ def test_masked_lm_rows_extension_gives_identical_results():
     staged = BatchPrefetcher("cuda:0").stage({k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()})
     c2 = model(**BatchPrefetcher("cuda:0").take(staged))
     assert c2["loss"].item() == a["loss"].item()
+
+
+def test_data_updating_optimizer_is_seen_by_the_compute_weights():
+    """the reference BertAdam updates `p.data` in place (optimization.py:293), which does not bump
+    Tensor._version. The bf16 compute copies are therefore refreshed on EVERY training-mode forward (one
+    vb_cast_multi launch): a step taken through `.data` must change the next forward's loss, and must match what a
+    freshly built model with the updated masters computes."""
+    model, cfg, sd, batch, c, gold = _build("small_ragged_pretraining", train=True)
+    model.bert._step = 100          # fixed dropout seed sequence for both models
+    l0 = model(**batch)["loss"]
+    l0.backward()
+    v0 = {n: p._version for n, p in model.named_parameters()}
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.grad is not None:
+                p.data.add_(-0.05 * p.grad.data.sign())   # sign-SGD through .data, like opt.py:293's p.data.add_
+    assert all(p._version == v0[n] for n, p in model.named_parameters()), "the update was meant to be invisible to _version"
+    model.zero_grad()
+    model.bert._step = 100
+    l1 = model(**batch)["loss"].item()
+    assert abs(l1 - l0.item()) > 1e-3 * abs(l0.item()), "stale compute weights: the loss did not move after the update"
+    # the same masters in a fresh model give the same loss
+    from visualbert_b200 import BertConfig, TrainVisualBERTObjective
+    fresh = TrainVisualBERTObjective(BertConfig.from_dict(cfg), c["head"], visual_embedding_dim=c["Dv"], **c.get("flags", {}))
+    fresh.load_state_dict(model.state_dict(), strict=False)
+    fresh.to(l0.device).train()
+    fresh.bert._step = 100
+    l2 = fresh(**batch)["loss"].item()
+    assert abs(l1 - l2) <= 1e-5 * abs(l2) + 1e-6
+    # eval mode keeps the cache until a version changes
+    model.eval()
+    e0 = model(**batch)["loss"].item()
+    g0 = model.bert._bank.generation
+    e1 = model(**batch)["loss"].item()
+    assert model.bert._bank.generation == g0 and e0 == e1
+    with torch.no_grad():
+        model.bert.encoder.layer[0].output.dense.weight.mul_(1.5)   # autograd-visible in-place op: version bump
+    e2 = model(**batch)["loss"].item()
+    assert model.bert._bank.generation == g0 + 1 and e2 != e1

@@ -65,13 +65,15 @@ AdamTensor = _struct("AdamTensor", [
     ("p", _P), ("g", _P), ("m", _P), ("v", _P), ("numel", c_i64), ("lr", c_f32), ("weight_decay", c_f32),
     ("first_chunk", c_int), ("reserved", c_int)])
 VB_ADAM_CHUNK = 32768
+CastItem = _struct("CastItem", [("src", _P), ("dst", _P), ("numel", c_i64), ("first_chunk", c_int), ("dst_fp32", c_int)])
+VB_CAST_CHUNK = 8192
 
 # every symbol include/vbert_b200.h declares (checked by tests/test_abi.py without a GPU)
 EXPORTS = [
     "vb_abi_version", "vb_last_error", "vb_launch_count", "vb_profile_enable", "vb_profile_read", "vb_gemm", "vb_layernorm_fwd", "vb_layernorm_bwd",
     "vb_attention_keep_bytes", "vb_attention_fwd", "vb_attention_bwd", "vb_mask_bias", "vb_cast_f32_to_bf16", "vb_cast_bf16_to_f32",
     "vb_colsum_bf16", "vb_cross_entropy_fwd", "vb_cross_entropy_bwd", "vb_layer_fwd", "vb_layer_bwd", "vb_embed_fwd", "vb_embed_bwd",
-    "vb_bert_adam_step",
+    "vb_bert_adam_step", "vb_cast_multi",
 ]
 
 

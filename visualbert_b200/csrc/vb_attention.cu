@@ -466,7 +466,7 @@ static int fill_params(AttnParams& p, const void* qkv, const float* mask_bias, v
 
 long long attn_keep_bytes(int B, int S, int A) {
     const long long nkb = (S + kBlk - 1) / kBlk;
-    return static_cast<long long>(B) * A * (nkb * kBlk) * nkb * 8;
+    return 2 * static_cast<long long>(B) * A * (nkb * kBlk) * nkb * 8;  // query-major words + their transpose (key-major)
 }
 
 int attn_fwd(const void* qkv, const float* mask_bias, void* ctx, float* lse, void* keep, int B, int S, int A, int H,
@@ -522,7 +522,18 @@ int attn_bwd(const void* qkv, const float* mask_bias, const void* ctx, const flo
         env_read = true;
     }
     dim3 grid((S + kBlk - 1) / kBlk, A, B);
-    if (static_cast<int>(grid.x) <= kMaxSub && !staged_only()) return attn_bwd_head(p, static_cast<int>(grid.x), st);
+    // VB_ATTN_BWD_IMPL = tc | head | staged: tcgen05 kernel by default (seq <= 192), then the whole-head mma.sync kernel
+    static int bimpl = -1;
+    if (bimpl < 0) {
+        const char* e = getenv("VB_ATTN_BWD_IMPL");
+        bimpl = e == nullptr ? 0 : (e[0] == 't' ? 0 : (e[0] == 's' ? 2 : 1));
+    }
+    if (bimpl == 0 && !staged_only() && attn_bwd_tc_supported(p)) {
+        rc = attn_delta(p, st);
+        if (rc) return rc;
+        return attn_bwd_tc(p, st);
+    }
+    if (bimpl <= 1 && static_cast<int>(grid.x) <= kMaxSub && !staged_only()) return attn_bwd_head(p, static_cast<int>(grid.x), st);
     const int nsub = static_cast<int>(grid.x) < kMaxSub ? static_cast<int>(grid.x) : kMaxSub;
     {   // algorithmic work of the backward = 2x forward (recompute not credited), split evenly over the two kernels
         ProfScope ps(st, PROF_ATTN_DQ, 4.0 * B * A * S * S * kHd, 1);

@@ -265,6 +265,10 @@ constexpr int kMaxSub = 4;  // 64-row tiles per resident stage
 int attn_fwd_head(const AttnParams& p, int nkb, cudaStream_t st);
 int attn_bwd_head(const AttnParams& p, int nkb, cudaStream_t st);
 int attn_keep_mask(const AttnParams& p, int nkb, cudaStream_t st);
+int attn_delta(const AttnParams& p, cudaStream_t st);
+// tcgen05 / TMEM / TMA backward (vb_attention_bwd_tc.cu), seq <= 192; needs p.drow = D (attn_delta)
+bool attn_bwd_tc_supported(const AttnParams& p);
+int attn_bwd_tc(const AttnParams& p, cudaStream_t st);
 // tcgen05 / TMEM / TMA forward (vb_attention_tc.cu), seq <= 192
 bool attn_fwd_tc_supported(const AttnParams& p);
 int attn_fwd_tc(const AttnParams& p, cudaStream_t st);

@@ -29,37 +29,62 @@ __device__ __forceinline__ void load_rows(uint32_t tiles, const bf16* base, long
 }
 
 // ------------------------------------------------------------------------------------------------
-// attention-probability dropout mask for the whole-head forward kernel: one thread per 64-bit word (query row, 64-key
-// block), 16 counter hashes -> 64 keep decisions of 8 random bits each (keep iff value >= thresh8). Drawing the bits
-// inside the attention kernel cost 65 us per layer at the benchmark shape (it is latency/issue bound and the hashing
-// was ~40 % of its instructions); this kernel has nothing else to do and runs at full issue rate (~20 us).
+// attention-probability dropout mask: one thread per 64-bit word (query row, 64-key block), 16 counter hashes -> 64 keep
+// decisions of 8 random bits each (keep iff value >= thresh8). Drawing the bits inside the attention kernels cost 65 us
+// per layer at the benchmark shape; this kernel has nothing else to do and runs at full issue rate (~20 us).
+// Two layouts are written: keep[(bh * np64 + q) * nkb + kb] (bit = key % 64; rows = queries: forward kernels, mma.sync
+// backward) and the transpose keepT[(bh * np64 + key) * nkb + qb] (bit = query % 64; rows = keys: the tcgen05 backward,
+// whose TMEM lanes are keys). A block is one 64 x 64 bit tile; the transpose is 64 warp ballots per 32 rows.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-attn_keep_mask_kernel(unsigned long long* __restrict__ keep, long long nwords, int nkb, int np64, int S, unsigned seed,
-                      unsigned thresh8) {
+__global__ void __launch_bounds__(64)
+attn_keep_mask_kernel(unsigned long long* __restrict__ keep, unsigned long long* __restrict__ keepT, int nkb, int np64, int S,
+                      unsigned seed, unsigned thresh8) {
     pdl_trigger();
     pdl_wait();
-    const long long w = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-    if (w >= nwords) return;
-    const int row = static_cast<int>((w / nkb) % np64);
-    if (row >= S) { keep[w] = ~0ull; return; }
-    // bit-sliced comparison: 8 hashes are the 8 bit-planes of 32 independent 8-bit random values v; keep iff v >= thresh8
-    // (MSB-first comparator: ~2 logic ops per plane for 32 decisions, instead of a byte-wise compare per hash)
-    const uint32_t base = static_cast<uint32_t>(w) * 16u;
-    uint32_t word[2];
+    const int kb = blockIdx.x % nkb, qb = (blockIdx.x / nkb) % nkb;
+    const long long bh = blockIdx.x / (nkb * nkb);
+    const int row = qb * 64 + threadIdx.x;
+    const long long w = (bh * np64 + row) * nkb + kb;
+    unsigned long long word = ~0ull;
+    if (row < S) {
+        // bit-sliced comparison: 8 hashes are the 8 bit-planes of 32 independent 8-bit random values v; keep iff v >= thresh8
+        // (MSB-first comparator: ~2 logic ops per plane for 32 decisions, instead of a byte-wise compare per hash)
+        const uint32_t base = static_cast<uint32_t>(w) * 16u;
+        uint32_t half_w[2];
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        uint32_t ge = 0u, eq = 0xffffffffu;
+        for (int half = 0; half < 2; ++half) {
+            uint32_t ge = 0u, eq = 0xffffffffu;
 #pragma unroll
-        for (int b = 7; b >= 0; --b) {
-            const uint32_t plane = mix32((base + half * 8 + b) ^ seed);
-            const uint32_t tb = 0u - ((thresh8 >> b) & 1u);  // all ones when the threshold bit is set
-            ge |= eq & plane & ~tb;                            // threshold bit 0, value bit 1: greater
-            eq &= ~(plane ^ tb);                               // still equal on this bit
+            for (int b = 7; b >= 0; --b) {
+                const uint32_t plane = mix32((base + half * 8 + b) ^ seed);
+                const uint32_t tb = 0u - ((thresh8 >> b) & 1u);  // all ones when the threshold bit is set
+                ge |= eq & plane & ~tb;                            // threshold bit 0, value bit 1: greater
+                eq &= ~(plane ^ tb);                               // still equal on this bit
+            }
+            half_w[half] = ge | eq;
         }
-        word[half] = ge | eq;
+        word = static_cast<unsigned long long>(half_w[0]) | (static_cast<unsigned long long>(half_w[1]) << 32);
     }
-    keep[w] = static_cast<unsigned long long>(word[0]) | (static_cast<unsigned long long>(word[1]) << 32);
+    keep[w] = word;
+    // transpose the warp's two 32 x 32 bit blocks (rows = this warp's queries, columns = keys 0-31 / 32-63 of the block)
+    // with a 5-round shuffle butterfly: afterwards lane l holds, for key l (resp. 32 + l), the bits of the warp's 32 queries
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    uint32_t t_lo = static_cast<uint32_t>(word), t_hi = static_cast<uint32_t>(word >> 32);
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        const uint32_t m0 = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
+        const uint32_t y_lo = __shfl_xor_sync(0xffffffffu, t_lo, j), y_hi = __shfl_xor_sync(0xffffffffu, t_hi, j);
+        if ((lane & j) == 0) {
+            t_lo = (t_lo & m0) | ((y_lo & m0) << j);
+            t_hi = (t_hi & m0) | ((y_hi & m0) << j);
+        } else {
+            t_lo = ((y_lo & ~m0) >> j) | (t_lo & ~m0);
+            t_hi = ((y_hi & ~m0) >> j) | (t_hi & ~m0);
+        }
+    }
+    uint32_t* kt32 = reinterpret_cast<uint32_t*>(keepT);
+    kt32[((bh * np64 + kb * 64 + lane) * nkb + qb) * 2 + wi] = t_lo;
+    kt32[((bh * np64 + kb * 64 + 32 + lane) * nkb + qb) * 2 + wi] = t_hi;
 }
 
 // one 64-key block of the forward pass for a 16-row warp tile (same math as the staged kernel)
@@ -626,8 +651,8 @@ int attn_keep_mask(const AttnParams& p, int nkb, cudaStream_t st) {
     const long long nwords = static_cast<long long>(p.B) * p.A * np64 * nkb;
     VB_REQUIRE(nwords * 16 < (1LL << 32), "attention dropout: mask counter space exceeded (B*A*S too large)");
     ProfScope ps(st, PROF_ATTN_FWD, 0.0, 1);
-    VB_CHECK_CUDA(launch_pdl(attn_keep_mask_kernel, dim3(static_cast<unsigned>((nwords + 255) / 256)), dim3(256), 0, st, p.keep,
-                             nwords, nkb, np64, p.S, p.drop_seed, p.drop_thresh16));
+    VB_CHECK_CUDA(launch_pdl(attn_keep_mask_kernel, dim3(static_cast<unsigned>(nwords / 64)), dim3(64), 0, st, p.keep, p.keep + nwords,
+                             nkb, np64, p.S, p.drop_seed, p.drop_thresh16));
     return 0;
 }
 
@@ -683,12 +708,19 @@ static int bwd_ps_smem(const AttnParams& p, int nkb, int* colsP) {
     return smem <= max_smem ? smem : 0;
 }
 
+// D[b, h, q] = sum_d dO * O  (the softmax-backward row term), HBM-bound pre-pass shared by the backward kernels
+int attn_delta(const AttnParams& p, cudaStream_t st) {
+    const long long rows = static_cast<long long>(p.B) * p.S;
+    ProfScope ps(st, PROF_ATTN_DQ, 1.0 * p.B * p.A * p.S * p.S * kHd, 1);
+    VB_CHECK_CUDA(launch_pdl(attn_delta_kernel, dim3(static_cast<int>((rows + 7) / 8)), dim3(256), 0, st, p.ctx, p.dctx, p.drow, p.B,
+                             p.S, p.A, p.H));
+    return 0;
+}
+
 int attn_bwd_head(const AttnParams& p, int nkb, cudaStream_t st) {
     {
-        const long long rows = static_cast<long long>(p.B) * p.S;
-        ProfScope ps(st, PROF_ATTN_DQ, 1.0 * p.B * p.A * p.S * p.S * kHd, 1);
-        VB_CHECK_CUDA(launch_pdl(attn_delta_kernel, dim3(static_cast<int>((rows + 7) / 8)), dim3(256), 0, st, p.ctx, p.dctx, p.drow, p.B,
-                                 p.S, p.A, p.H));
+        int rc0 = attn_delta(p, st);
+        if (rc0) return rc0;
     }
     const int nw = (p.S + 15) / 16;
     int rc, colsP = 0;

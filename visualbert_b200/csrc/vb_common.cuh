@@ -236,19 +236,33 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug traps (kernel fails with an error the host reports) instead of
-// hanging the GPU. ~4e9 cycles ≈ 2 s at 1.9 GHz, far beyond any legitimate wait in these kernels.
+// Bounded wait: a protocol bug traps (the kernel fails with an error the host reports) instead of hanging the GPU:
+// ~4e9 cycles ≈ 2 s at 1.9 GHz, far beyond any legitimate wait in these kernels. Kept tiny and fully inline — the
+// hot kernels wait at dozens of sites (code size = instruction-cache misses on every role switch), and a shared
+// out-of-line helper would make ptxas apply the SMALLEST setmaxnreg budget of its callers to all of them.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 0x3ffu) == 0 && clock64() - t0 > 4000000000ll) {
-            printf("vbert_b200: mbarrier wait timeout (block %d thread %d bar 0x%x parity %u)\n",
-                   blockIdx.x, threadIdx.x, bar, parity);
-            __trap();
-        }
+        if ((++spins & 0x3ffu) == 0 && clock64() - t0 > 4000000000ll) __trap();
     }
+}
+
+// UMMA shared-memory descriptor split in two 32-bit halves: only the 14-bit start-address field (bits 0-13, in 16-byte
+// units) changes between the MMAs of a tile, so stepping through k is ONE 32-bit add on the low half — the MMA-issuing
+// thread is a single thread whose instruction latency is exposed, every instruction saved there shortens the pipeline.
+struct UmmaDesc {
+    uint32_t lo, hi;
+    __device__ __forceinline__ uint64_t at(uint32_t byte_off) const {
+        return (static_cast<uint64_t>(hi) << 32) | static_cast<uint64_t>(lo + (byte_off >> 4));
+    }
+};
+__device__ __forceinline__ UmmaDesc make_umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    UmmaDesc d;
+    d.lo = ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+    d.hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);   // version 1 (bit 46), SWIZZLE_128B (bits 61-63)
+    return d;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -371,6 +385,12 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -396,9 +416,18 @@ __device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t
                  "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                  : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x32b_x4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
+// Register re-distribution between warp roles (whole warpgroups of 4 warps): the control warpgroup shrinks its
+// allocation, the element-wise warpgroups grow theirs; ptxas compiles the code that follows against the new limit.
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

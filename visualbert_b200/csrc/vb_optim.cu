@@ -130,9 +130,61 @@ int bert_adam_step(const vb_adam_tensor* table, int n_tensors, int n_chunks, flo
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// multi-tensor cast: the bf16 compute copies of ALL weight matrices (and fp32 copies of the packed qkv biases) of a
+// model are refreshed by one launch over a device table — the caller does this at the start of every training-mode
+// forward, so any optimizer that updates the fp32 masters (in place, through .data, fused, ...) is picked up.
+// ---------------------------------------------------------------------------------------------
+constexpr int kCastChunk = VB_CAST_CHUNK;
+__global__ void __launch_bounds__(256)
+cast_multi_kernel(const vb_cast_item* __restrict__ tab, int n_items) {
+    int lo = 0, hi = n_items - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (tab[mid].first_chunk <= static_cast<int>(blockIdx.x)) lo = mid; else hi = mid - 1;
+    }
+    const vb_cast_item e = tab[lo];
+    const long long begin = static_cast<long long>(blockIdx.x - e.first_chunk) * kCastChunk;
+    const long long end = min(begin + kCastChunk, static_cast<long long>(e.numel));
+    const float* src = static_cast<const float*>(e.src);
+    if (e.dst_fp32) {
+        float* dst = static_cast<float*>(e.dst);
+        for (long long i = begin + threadIdx.x; i < end; i += 256) dst[i] = src[i];
+        return;
+    }
+    bf16* dst = static_cast<bf16*>(e.dst);
+    if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+        const long long v8_end = begin + ((end - begin) & ~7LL);
+        for (long long i = begin + threadIdx.x * 8LL; i < v8_end; i += 256 * 8LL) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src + i));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(src + i + 4));
+            uint4 u;
+            u.x = pack_bf16x2(a.x, a.y); u.y = pack_bf16x2(a.z, a.w);
+            u.z = pack_bf16x2(b.x, b.y); u.w = pack_bf16x2(b.z, b.w);
+            *reinterpret_cast<uint4*>(dst + i) = u;
+        }
+        for (long long i = v8_end + threadIdx.x; i < end; i += 256) dst[i] = __float2bfloat16_rn(src[i]);
+    } else {
+        for (long long i = begin + threadIdx.x; i < end; i += 256) dst[i] = __float2bfloat16_rn(src[i]);
+    }
+}
+
+int cast_multi(const vb_cast_item* table, int n_items, int n_chunks, cudaStream_t st) {
+    VB_REQUIRE(table != nullptr && n_items > 0 && n_chunks > 0, "vb_cast_multi: empty table");
+    {
+        ProfScope ps(st, PROF_OTHER, 0.0, 1);
+        cast_multi_kernel<<<n_chunks, 256, 0, st>>>(table, n_items);
+    }
+    VB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace vb
 
 extern "C" {
+int vb_cast_multi(const vb_cast_item* table, int32_t n_items, int32_t n_chunks, void* stream) {
+    return vb::cast_multi(table, n_items, n_chunks, static_cast<cudaStream_t>(stream));
+}
 int vb_bert_adam_step(const vb_adam_tensor* table, int32_t n_tensors, int32_t n_chunks, float* sumsq, double b1, double b2,
                       double eps, double max_grad_norm, void* stream) {
     return vb::bert_adam_step(table, n_tensors, n_chunks, sumsq, b1, b2, eps, max_grad_norm, static_cast<cudaStream_t>(stream));

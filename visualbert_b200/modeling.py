@@ -180,7 +180,7 @@ class BertLayer(nn.Module):
         meta = dict(heads=self.attention.self.num_attention_heads, layer_index=self.layer_index,
                     hidden_dropout=self.hidden_dropout_prob if train else 0.0,
                     attn_dropout=self.attention_probs_dropout_prob if train else 0.0,
-                    seed=int(seed), cache=self._weights)
+                    seed=int(seed), cache=self._weights, train=train)
         return ops.bert_layer(hidden_states.to(torch.bfloat16), attention_mask.float().contiguous(), meta, self._params())
 
     @torch.no_grad()
@@ -274,7 +274,8 @@ class BertEmbeddingsWithVisualEmbedding(nn.Module):
             token_type_ids = torch.zeros_like(input_ids)
         if visual_embeddings is not None and visual_embeddings_type is None:
             visual_embeddings_type = torch.zeros(visual_embeddings.shape[:-1], dtype=torch.long, device=input_ids.device)
-        meta = dict(dropout=self.hidden_dropout_prob if self.training else 0.0, seed=int(seed), cache=self._weights)
+        meta = dict(dropout=self.hidden_dropout_prob if self.training else 0.0, seed=int(seed), cache=self._weights,
+                    train=self.training)
         return ops.bert_embeddings(
             meta, input_ids, token_type_ids, visual_embeddings_type, visual_embeddings,
             self.word_embeddings.weight, self.position_embeddings.weight, self.token_type_embeddings.weight,
@@ -443,6 +444,56 @@ class BertVisualModel(PreTrainedBertModel):
         self._step = 0
         self.dropout_seed = 0x5EED
 
+    def _bank_sources(self):
+        layers = list(self.encoder.layer) + ([self.additional_layer] if self.bypass_transformer else [])
+        srcs = []
+        for l in layers:
+            a = l.attention
+            srcs += [a.self.query.weight, a.self.key.weight, a.self.value.weight, a.output.dense.weight, l.intermediate.dense.weight,
+                     l.output.dense.weight, a.self.query.bias, a.self.key.bias, a.self.value.bias]
+        srcs.append(self.embeddings.projection.weight)
+        extra = self.__dict__.get("_bank_extra")
+        if extra is not None:
+            srcs += list(extra[0])
+        return layers, srcs
+
+    def refresh_compute_weights(self):
+        """bf16 compute copies of all matrices of the encoder path <- fp32 masters, ONE launch (ops.WeightBank). Always
+        in training mode (any optimizer, including the reference BertAdam's `p.data` updates, is picked up), on a
+        version change in eval mode. Called by forward(); public so callers that edit weights mid-eval can force it."""
+        layers, srcs = self._bank_sources()
+        if not srcs[0].is_cuda:
+            return
+        bank = self.__dict__.get("_bank")
+        if bank is None or not bank.bound_to(srcs):
+            bf16, dev = torch.bfloat16, srcs[0].device
+            bank = ops.WeightBank()
+            items, keep = [], []
+            for l in layers:
+                a = l.attention
+                H, I = a.output.dense.weight.shape[0], l.intermediate.dense.weight.shape[0]
+                wqkv = torch.empty(3 * H, H, device=dev, dtype=bf16)
+                wo = torch.empty(H, H, device=dev, dtype=bf16)
+                wi = torch.empty(I, H, device=dev, dtype=bf16)
+                wout = torch.empty(H, I, device=dev, dtype=bf16)
+                bqkv = torch.empty(3 * H, device=dev, dtype=torch.float32)
+                items += [(a.self.query.weight, wqkv[0:H], False), (a.self.key.weight, wqkv[H:2 * H], False),
+                          (a.self.value.weight, wqkv[2 * H:], False), (a.output.dense.weight, wo, False),
+                          (l.intermediate.dense.weight, wi, False), (l.output.dense.weight, wout, False),
+                          (a.self.query.bias, bqkv[0:H], True), (a.self.key.bias, bqkv[H:2 * H], True),
+                          (a.self.value.bias, bqkv[2 * H:], True)]
+                l._weights.buf, l._weights.bank = (wqkv, wo, wi, wout, bqkv), bank
+            pw = self.embeddings.projection.weight
+            pbuf = torch.empty(pw.shape, device=dev, dtype=bf16)
+            items.append((pw, pbuf, False))
+            self.embeddings._weights.buf, self.embeddings._weights.bank = pbuf, bank
+            extra = self.__dict__.get("_bank_extra")
+            if extra is not None:
+                items += extra[1](bank)
+            bank.bind(items, keep)
+            self.__dict__["_bank"] = bank
+        bank.refresh(force=self.training)
+
     def next_seed(self):
         """Per-forward dropout seed: forward and backward of one step share it; steps differ."""
         self._step += 1
@@ -457,6 +508,7 @@ class BertVisualModel(PreTrainedBertModel):
         if token_type_ids is None:
             token_type_ids = torch.zeros_like(input_ids)
         seed = self.next_seed() if self.training else 0
+        self.refresh_compute_weights()
         bias = ops.mask_bias(attention_mask, None)
         x = self.embeddings(input_ids, token_type_ids, visual_embeddings=visual_embeddings,
                             visual_embeddings_type=visual_embeddings_type, position_embeddings_visual=position_embeddings_visual,
@@ -609,6 +661,29 @@ class TrainVisualBERTObjective(PreTrainedBertModel):
         BEFORE the encoder is enqueued (the stream is empty then) instead of draining ~12 ms of queued work later."""
         return torch.nonzero(flat_labels.contiguous().view(-1) != -1).squeeze(1)
 
+    def _decoder_cache(self):
+        """The tied decoder table rides the encoder's WeightBank (refreshed by the same launch, before the encoder runs)."""
+        dw = self.__dict__.get("_decoder_weights")
+        if dw is None:
+            dw = ops.DecoderWeights()
+            self.__dict__["_decoder_weights"] = dw
+        return dw
+
+    def _register_decoder_in_bank(self):
+        if self.training_head_type != "pretraining" or not hasattr(self, "cls"):
+            return
+        head = self.cls.predictions
+        E, b = head.decoder.weight, head.bias
+
+        def items(bank):
+            dw = self._decoder_cache()
+            table, bias_p = dw.alloc(E)
+            dw.bank = bank
+            V = E.shape[0]
+            return [(E, table[:V], False), (b, bias_p[:V], True)]
+
+        self.bert.__dict__["_bank_extra"] = ((E, b), items)
+
     def _masked_lm_loss(self, sequence_output, flat_labels, rows=None):
         """CrossEntropyLoss(ignore_index=-1) of the MLM head (M.py:1471-1473) evaluated on the labelled rows only:
         ignored rows contribute neither to the sum nor to the count, so value and gradients are unchanged."""
@@ -622,9 +697,7 @@ class TrainVisualBERTObjective(PreTrainedBertModel):
         # decoder + loss on the library's kernels: tcgen05 GEMMs (fwd / dgrad / wgrad into the tied word-embedding
         # gradient) and the fused cross-entropy; the small transform (dense + gelu + LayerNorm on ~12 % of the rows)
         # stays PyTorch
-        if not hasattr(self, "_decoder_weights"):
-            self._decoder_weights = ops.DecoderWeights()
-        scores = ops.mlm_decoder(head.transform(hidden), head.decoder.weight, head.bias, self._decoder_weights)
+        scores = ops.mlm_decoder(head.transform(hidden), head.decoder.weight, head.bias, self._decoder_cache(), self.training)
         return ops.cross_entropy_rows(scores, labels.index_select(0, rows), head.decoder.weight.size(0))
 
     def forward(self, input_ids, token_type_ids, input_mask, visual_embeddings, position_embeddings_visual, image_mask,
@@ -635,6 +708,8 @@ class TrainVisualBERTObjective(PreTrainedBertModel):
         (b * (T + V) + t, int64, on the device) of the positions whose `masked_lm_labels` is not -1. When given (e.g. by
         `parallel.BatchPrefetcher`, which computes them on the host from the host copy of the labels) the forward pass
         contains no host synchronisation at all; when omitted they are found with one `nonzero` before the encoder."""
+        if "_bank_extra" not in self.bert.__dict__:
+            self._register_decoder_in_bank()
         flat_input_ids = transform_to_batch_sequence(input_ids)
         flat_token_type_ids = transform_to_batch_sequence(token_type_ids)
         flat_input_mask = transform_to_batch_sequence(input_mask)

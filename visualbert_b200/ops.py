@@ -79,13 +79,17 @@ def mask_bias(input_mask, image_mask):
 
 
 def _grad_targets(params, adjacent_groups=()):
-    """Direct-accumulate mode: when every parameter already owns a contiguous fp32 `.grad` (e.g. views of a
-    FlatGradSync buffer) — and the parameters of each adjacent group are laid out back to back — the kernels add
-    their results straight into those buffers (all gradient outputs of the C ABI are `+=`), and autograd gets
-    None. Otherwise returns None and the caller allocates fresh zero buffers for autograd to accumulate."""
+    """Direct-accumulate mode — OPT-IN: only parameters a gradient owner has flagged with `_vb_direct_grad = True`
+    (parallel.FlatGradSync does, for the views of its flat buffer) get their gradients written straight into `.grad`
+    by the kernels (all gradient outputs of the C ABI are `+=`), with autograd receiving None. Everyone else — plain
+    optimizers, DDP with gradient_as_bucket_view, tensor / post-accumulate hooks, torch.autograd.grad — goes through
+    AccumulateGrad as usual: the caller allocates fresh zero buffers and returns them to autograd.
+    Additionally every `.grad` must be a contiguous fp32 tensor of the parameter's shape, and the parameters of each
+    adjacent group must be laid out back to back."""
     for p in params:
         g = p.grad
-        if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.device != p.device or g.shape != p.shape:
+        if (not getattr(p, "_vb_direct_grad", False) or g is None or g.dtype != torch.float32 or not g.is_contiguous()
+                or g.device != p.device or g.shape != p.shape):
             return None
     for group in adjacent_groups:
         for a, b in zip(group[:-1], group[1:]):
@@ -94,16 +98,76 @@ def _grad_targets(params, adjacent_groups=()):
     return [p.grad for p in params]
 
 
+class WeightBank:
+    """Every bf16 compute copy the CUDA path reads (packed q|k|v, attention-output, FFN matrices of all layers, the visual
+    projection, the tied MLM decoder table) plus the fp32 packed q|k|v biases, refreshed from the fp32 master
+    parameters by ONE vb_cast_multi launch.
+
+    `refresh(force=True)` is called at the start of every training-mode forward: the masters may have been changed by
+    anything — the reference BertAdam updates through `p.data` (optimization.py:293), which does not bump
+    `Tensor._version`, so version-keyed caching alone would silently train on stale bf16 weights. In eval mode the copy
+    is redone only when a (data_ptr, _version) signature changed (load_state_dict, manual edits through autograd-visible
+    ops)."""
+
+    def __init__(self):
+        self.sig = None
+        self.items = []       # (src parameter, dst tensor, dst_is_fp32)
+        self.table = None
+        self.n_chunks = 0
+        self.keep = []        # owners of the dst storage
+        self.generation = 0
+
+    def _signature(self, params):
+        return tuple((p.data_ptr(), p._version) for p in params)
+
+    def bind(self, items, keep):
+        """items: list of (src fp32 parameter, dst tensor [contiguous view], dst_is_fp32)."""
+        import numpy as np
+        self.items = items
+        self.keep = keep
+        arr = (_lib.CastItem * len(items))()
+        chunk = 0
+        for i, (src, dst, f32) in enumerate(items):
+            assert src.dtype == torch.float32 and src.is_contiguous() and dst.is_contiguous() and dst.numel() == src.numel()
+            arr[i].src, arr[i].dst, arr[i].numel = src.data_ptr(), dst.data_ptr(), src.numel()
+            arr[i].first_chunk, arr[i].dst_fp32 = chunk, 1 if f32 else 0
+            chunk += (src.numel() + _lib.VB_CAST_CHUNK - 1) // _lib.VB_CAST_CHUNK
+        self.n_chunks = chunk
+        raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
+        self.table = torch.from_numpy(raw).to(items[0][0].device)
+        self.ptrs = tuple(src.data_ptr() for src, _, _ in items)
+        self.sig = None
+
+    def bound_to(self, params):
+        return self.table is not None and self.ptrs == tuple(p.data_ptr() for p in params)
+
+    def refresh(self, force):
+        srcs = [s_ for s_, _, _ in self.items]
+        sig = self._signature(srcs)
+        if not force and sig == self.sig:
+            return
+        with torch.cuda.device(self.table.device):
+            _lib.check(_lib.lib().vb_cast_multi(ctypes.c_void_p(self.table.data_ptr()), len(self.items), self.n_chunks, _stream()),
+                       "vb_cast_multi")
+        self.sig = sig
+        self.generation += 1
+
+
 class LayerWeights:
-    """bf16 compute copies of one BertLayer's matrices, refreshed when the fp32 masters change."""
+    """bf16 compute copies of one BertLayer's matrices. Normally views into the model's WeightBank (refreshed once per
+    forward by the model); a stand-alone BertLayer refreshes them itself — on every training-mode forward, or when the
+    masters' (data_ptr, _version) signature changes in eval mode."""
 
     def __init__(self):
         self.key = None
         self.buf = None
+        self.bank = None      # set by the owning model: buffers are bank views, refresh is the bank's job
 
-    def get(self, q, k, v, o, w1, w2, bq, bk, bv):
+    def get(self, q, k, v, o, w1, w2, bq, bk, bv, train=False):
+        if self.bank is not None:
+            return self.buf
         key = tuple((p.data_ptr(), p._version) for p in (q, k, v, o, w1, w2, bq, bk, bv))
-        if key != self.key:
+        if train or key != self.key:
             H, I = o.shape[0], w1.shape[0]
             dev = q.device
             if self.buf is None or self.buf[0].device != dev:
@@ -136,7 +200,7 @@ class _LayerFn(torch.autograd.Function):
         A = meta["heads"]
         dev = x.device
         x = x.contiguous()
-        wqkv, wo, wi, wout, bqkv = meta["cache"].get(qw, kw, vw, ow, iw, dw, qb, kb, vb)
+        wqkv, wo, wi, wout, bqkv = meta["cache"].get(qw, kw, vw, ow, iw, dw, qb, kb, vb, train=meta.get("train", False))
         f32 = torch.float32
         acts = dict(
             qkv=torch.empty(M, 3 * H, device=dev, dtype=_BF16), ctx=torch.empty(M, H, device=dev, dtype=_BF16),
@@ -162,7 +226,7 @@ class _LayerFn(torch.autograd.Function):
         ctx.acts = acts
         ctx.params = (qw, qb, kw, kb, vw, vb, ow, ob, g1, b1, iw, ib, dw, db, g2, b2)
         ctx.weights = (wqkv, wo, wi, wout, bqkv)
-        ctx.weight_key = meta["cache"].key
+        ctx.weight_key = meta["cache"].key if meta["cache"].bank is None else None
         ctx.save_for_backward(x, mbias, ob, g1, b1, ib, db, g2, b2)
         return y
 
@@ -170,7 +234,7 @@ class _LayerFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, mbias, ob, g1, b1, ib, db, g2, b2 = ctx.saved_tensors
         meta, acts = ctx.meta, ctx.acts
-        if meta["cache"].key != ctx.weight_key:
+        if ctx.weight_key is not None and meta["cache"].key != ctx.weight_key:
             raise RuntimeError("visualbert_b200: layer weights were modified between forward and backward")
         wqkv, wo, wi, wout, bqkv = ctx.weights
         B, S, H = x.shape
@@ -225,10 +289,13 @@ class ProjectionWeights:
     def __init__(self):
         self.key = None
         self.buf = None
+        self.bank = None
 
-    def get(self, w):
+    def get(self, w, train=False):
+        if self.bank is not None:
+            return self.buf
         key = (w.data_ptr(), w._version)
-        if key != self.key:
+        if train or key != self.key:
             with torch.no_grad():
                 self.buf = cast_to_bf16(w.detach(), self.buf if self.buf is not None and self.buf.device == w.device else None)
             self.key = key
@@ -254,7 +321,7 @@ class _EmbedFn(torch.autograd.Function):
             vt = visual_type.to(torch.int64).contiguous()
             f = feats.reshape(B * V, Dv)
             fb = cast_to_bf16(f) if f.dtype == torch.float32 else f.to(_BF16).contiguous()
-            wp = meta["cache"].get(pw)
+            wp = meta["cache"].get(pw, train=meta.get("train", False))
             vis_proj = torch.empty(B * V, H, device=dev, dtype=_BF16)
             xb = None if vis_extra is None else vis_extra.detach().reshape(B * V, H).to(_BF16).contiguous()
         else:
@@ -359,10 +426,21 @@ class DecoderWeights:
         self.key = None
         self.table = None
         self.bias = None
+        self.bank = None
 
-    def get(self, E, bias):
+    def alloc(self, E):
+        V = E.shape[0]
+        Vp = (V + 15) // 16 * 16
+        if self.table is None or self.table.device != E.device or self.table.shape[0] != Vp:
+            self.table = torch.zeros(Vp, E.shape[1], device=E.device, dtype=_BF16)
+            self.bias = torch.full((Vp,), -30000.0, device=E.device, dtype=torch.float32)
+        return self.table, self.bias
+
+    def get(self, E, bias, train=False):
+        if self.bank is not None:
+            return self.table, self.bias
         key = (E.data_ptr(), E._version, bias.data_ptr(), bias._version)
-        if key != self.key:
+        if train or key != self.key:
             V = E.shape[0]
             Vp = (V + 15) // 16 * 16
             with torch.no_grad():
@@ -383,12 +461,12 @@ class _MlmDecoderFn(torch.autograd.Function):
     into the (tied) word-embedding gradient when that buffer exists."""
 
     @staticmethod
-    def forward(ctx, t, E, bias, cache):
+    def forward(ctx, t, E, bias, cache, train=False):
         _require_cuda(t, "mlm_decoder")
         n, H = t.shape
         V = E.shape[0]
         Vp = (V + 15) // 16 * 16
-        table, bias_p = cache.get(E, bias)
+        table, bias_p = cache.get(E, bias, train=train)
         t = t.to(_BF16).contiguous()
         logits = torch.empty(n, Vp, device=t.device, dtype=_BF16)
         _gemm(A=t.data_ptr(), lda=H, B=table.data_ptr(), ldb=H, M=n, N=Vp, K=H, D=logits.data_ptr(), ldd=Vp,
@@ -419,12 +497,12 @@ class _MlmDecoderFn(torch.autograd.Function):
                                              n, Vp, _stream()), "vb_colsum_bf16")
         if direct is not None:
             db.add_(db_pad[:V])
-            return dt, None, None, None
-        return dt, dE, db_pad[:V].clone(), None
+            return dt, None, None, None, None
+        return dt, dE, db_pad[:V].clone(), None, None
 
 
-def mlm_decoder(t, E, bias, cache):
-    return _MlmDecoderFn.apply(t, E, bias, cache)
+def mlm_decoder(t, E, bias, cache, train=False):
+    return _MlmDecoderFn.apply(t, E, bias, cache, train)
 
 
 class _CrossEntropyFn(torch.autograd.Function):

@@ -12,7 +12,11 @@ import torch.distributed as dist
 
 
 class FlatGradSync:
-    def __init__(self, module, process_group=None):
+    def __init__(self, module, process_group=None, reduce_dtype=torch.float32):
+        """reduce_dtype: torch.float32 (default: exact sum of the ranks' fp32 gradients) or torch.bfloat16 (half the
+        bytes on the wire; the sum is rounded to bf16 — an explicit opt-in, not reference semantics)."""
+        self.reduce_dtype = reduce_dtype
+        self._wire = None
         seen, self.params = set(), []
 
         def add(p):
@@ -50,6 +54,7 @@ class FlatGradSync:
         for p, o in zip(self.params, offsets):
             v = self.flat[o: o + p.numel()].view_as(p)
             p.grad = v
+            p._vb_direct_grad = True   # opt in: the backward kernels accumulate straight into this view (ops._grad_targets)
             self.views.append(v)
 
     def zero(self):
@@ -59,11 +64,30 @@ class FlatGradSync:
             if p.grad is not v:
                 p.grad = v
 
-    def allreduce(self):
-        """The single collective of the step. No-op for a lone process."""
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-            self.flat.div_(dist.get_world_size(self.group))
+    def world_size(self):
+        return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
+    def loss_scale(self):
+        """1 / world_size. Multiply the loss by it before backward() and call allreduce(prescaled=True): the mean over
+        ranks (reference: `loss.mean()` over DataParallel replicas, model_wrapper.py:75) then costs no extra pass over
+        the 440 MB buffer."""
+        return 1.0 / self.world_size()
+
+    def allreduce(self, prescaled=False):
+        """The single collective of the step (sum over ranks; divided by the world size unless the loss was already
+        scaled by loss_scale()). No-op for a lone process."""
+        n = self.world_size()
+        if n > 1:
+            if self.reduce_dtype == torch.float32:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            else:
+                if self._wire is None:
+                    self._wire = torch.empty(self.flat.numel(), device=self.flat.device, dtype=self.reduce_dtype)
+                self._wire.copy_(self.flat)
+                dist.all_reduce(self._wire, op=dist.ReduceOp.SUM, group=self.group)
+                self.flat.copy_(self._wire)
+            if not prescaled:
+                self.flat.div_(n)
         return self.flat
 
 
