@@ -139,11 +139,22 @@ def cpu_oracle_step_time(c, sample_b, steps, warmup, threads=None):
 
     for _ in range(warmup):
         step()
-    t0 = time.perf_counter()
+    times = []
     for _ in range(steps):
+        t0 = time.perf_counter()
         step()
-    dt = (time.perf_counter() - t0) / max(steps, 1)
-    return dt, torch.get_num_threads()
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    dt = sum(times) / max(len(times), 1)
+    spread = {"min_ms": 1e3 * times[0], "median_ms": 1e3 * times[len(times) // 2], "max_ms": 1e3 * times[-1], "steps": len(times)}
+    return dt, torch.get_num_threads(), spread
+
+
+def cpu_threads():
+    """Threads for the CPU arm: one per physical core (the box exposes 2 hardware threads per core), set EXPLICITLY —
+    under torch.distributed.run OMP_NUM_THREADS defaults to 1, which made the N>1 reference lines incomparable."""
+    n = os.cpu_count() or 2
+    return max(1, min(64, n // 2))
 
 
 def run_reference(args):
@@ -152,7 +163,7 @@ def run_reference(args):
         return 0
     c = build_cfg(args.config)
     sample_b = args.cpu_sample
-    dt, threads = cpu_oracle_step_time(c, sample_b, args.steps, args.warmup)
+    dt, threads, spread = cpu_oracle_step_time(c, sample_b, max(args.steps, 5), args.warmup, threads=cpu_threads())
     value = sample_b / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -161,7 +172,7 @@ def run_reference(args):
         "config": {"workload": workload_name(c), "global_batch": sample_b,
                    "note": "reference arithmetic on host cores: oracle port of modeling.py (the Python reference itself "
                            "is not present on the GPU box); each step is a bounded sample of the workload"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "spread": spread,
                          "sample": f"{sample_b} pairs/step fwd+bwd, fp32, {os.cpu_count()} logical CPUs, {threads} torch threads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -322,6 +333,43 @@ def run_ours(args):
                     "roofline": {"bound": "hbm", "achieved": opt_bytes / (ms_opt * 1e-3) / 1e9, "unit": "GB/s",
                                  "bytes_per_param": 32}}
 
+    # ---- the other BASELINE.json configs at their per-GPU batch (global batch / 8), same step, same all-reduce ----
+    others = None
+    had_opt = opt is not None
+    if (world > 1 or args.other_configs) and args.config == "cfg2" and not args.batch:
+        model = sync = opt = resident = pf = None   # release the cfg2 replica (weights, flat gradients, optimizer state)
+        torch.cuda.empty_cache()
+        others = {}
+        for name in ("cfg3", "cfg4", "cfg5"):
+            oc = build_cfg(name)
+            ocfg = synthetic.bert_config_dict(oc["layers"], oc["hidden"], oc["heads"], oc["inter"])
+            torch.manual_seed(0)
+            m2 = TrainVisualBERTObjective(BertConfig.from_dict(ocfg), oc["head"], visual_embedding_dim=oc["Dv"])
+            m2.bert.embeddings.special_intialize()
+            m2.to(dev).train()
+            s2 = FlatGradSync(m2)
+            hb = synthetic.make_batch(oc["B"], oc["T"], oc["V"], oc["Dv"], head=oc["head"], seed=1234 + rank,
+                                      nlvr_types=(oc["head"] == "nlvr"))
+            pf2 = BatchPrefetcher(dev)
+            res2 = pf2.take(pf2.stage({k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in hb.items()}))
+
+            def step2():
+                s2.zero()
+                out = m2(**res2)
+                (out["loss"] * lscale if world > 1 else out["loss"]).backward()
+                s2.allreduce(prescaled=True)
+
+            for _ in range(3):
+                step2()
+            k2 = max(3, min(args.steps, 10))
+            ms2 = timed(step2, k2) / k2
+            others[name] = {"workload": workload_name(oc), "per_gpu_batch": oc["B"], "global_batch": world * oc["B"],
+                            "seq_len": oc["T"] + oc["V"], "ms_per_step": ms2, "value": world * oc["B"] / (ms2 * 1e-3), "unit": UNIT,
+                            "step_roofline_frac": (oc["B"] / (ms2 * 1e-3)) * hot_path_flops_per_pair(oc) / 1e12 / load_peaks()["bf16_sustained"],
+                            "steps": k2}
+            del m2, s2, res2, pf2
+            torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -348,7 +396,7 @@ def run_ours(args):
         "config": {"workload": workload_name(c), "global_batch": world * B, "per_gpu_batch": B, "seq_len": c["T"] + c["V"],
                    "parallelism": f"dp{world}", "mode": "train (dropout 0.1 active)",
                    "step": "zero_grad + forward (MLM+NSP heads) + backward" + (" + 1 NCCL all-reduce (flat fp32 grads)" if world > 1 else "")
-                           + ("; + fused BertAdam step (--optimizer; NOT the BASELINE metric)" if opt is not None
+                           + ("; + fused BertAdam step (--optimizer; NOT the BASELINE metric)" if had_opt
                               else "; optimizer excluded (BASELINE.md §2)"),
                    "l2": "per-step working set (>12 GB of activations) is >> the 126 MB L2; no explicit flush needed"},
         "clocks": clk.summary(),
@@ -356,7 +404,8 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_2cta_kernel (all 12 GEMMs/layer fwd+dgrad+wgrad, projection, MLM decoder)",
                      "achieved": gemm_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                      "frac": gemm_tf / peaks["bf16_sustained"], "traffic": traffic,
-                     "traffic_note": ("DRAM read+write bytes per GEMM launch (ncu --set full, mean over one layer's 12 GEMM launches), "
+                     "traffic_note": ("NOT measured in this run: DRAM read+write bytes per GEMM launch from the committed ncu capture "
+                                      "(ncu --set full, mean over one layer's 12 GEMM launches), "
                                       + traffic_src) if traffic else "no ncu capture for this workload",
                      "flops_per_launch": g["work"] / max(1, g["launches"]),
                      "of": peaks["source"] + " bf16_tflops_sustained", "launches_per_step": g["launches"] / args.steps,
@@ -372,10 +421,12 @@ def run_ours(args):
     }
     if opt_info is not None:
         line["optimizer"] = opt_info
+    if others is not None:
+        line["other_configs"] = others
     if world == 1 and not args.no_cpu_baseline:
-        dt, threads = cpu_oracle_step_time(c, args.cpu_sample, 2, 1)
-        line["cpu_baseline"] = {"value": args.cpu_sample / dt, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"{args.cpu_sample} pairs/step x 2 steps fwd+bwd of the same workload, fp32 oracle, "
+        dt, threads, spread = cpu_oracle_step_time(c, args.cpu_sample, 5, 1, threads=cpu_threads())
+        line["cpu_baseline"] = {"value": args.cpu_sample / dt, "unit": UNIT, "cores": threads, "kind": "port", "spread": spread,
+                                "sample": f"{args.cpu_sample} pairs/step x 5 steps fwd+bwd of the same workload, fp32 oracle, "
                                           f"{os.cpu_count()} logical CPUs, {threads} torch threads"}
     print(json.dumps(line))
     if world > 1:
@@ -393,6 +444,8 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch override (parity/debug only)")
     ap.add_argument("--cpu-sample", type=int, default=8, help="pairs per CPU step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--other-configs", action="store_true",
+                    help="also time BASELINE.json configs[2..4] at their per-GPU batch (always on for N > 1)")
     ap.add_argument("--optimizer", action="store_true",
                     help="also run the fused BertAdam step every step (SURVEY §8f rank 2; the BASELINE metric excludes it)")
     args = ap.parse_args()

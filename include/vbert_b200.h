@@ -188,6 +188,24 @@ int vb_layer_fwd(const vb_layer_desc* d, const void* x_in, void* x_out, const vb
 int vb_layer_bwd(const vb_layer_desc* d, const void* x_in, const vb_layer_acts* acts, const void* dy, void* dx,
                  const vb_layer_grads* grads, const vb_layer_scratch* scratch, void* stream);
 
+/* ---- BertEncoder (M.py:344-371): the whole layer stack in ONE call -------------------------------------------
+ * The per-layer activations (everything vb_layer_acts names, plus each layer's output) live in ONE caller-owned arena
+ * whose layout the library defines: vb_encoder_arena_layout fills the byte offsets of the 14 per-layer buffers inside a
+ * layer slot (order: qkv, ctx, lse, pre1, mean1, rstd1, x1, u, g, pre2, mean2, rstd2, keep_mask, y) and returns the
+ * slot stride; layer l's buffer i sits at arena + l * stride + offsets[i]; total size = n_layers * stride. The same
+ * arena pointer is handed to forward and backward (PyTorch owns it; the library allocates nothing). One call replaces
+ * the Python loop of M.py:365-368 and its per-layer allocations: host time per step drops from ~5 ms to ~0.2 ms, and the
+ * recurring pointers make the library's tensor-map cache hit.
+ * descs[l].seed / dropouts / layer_index are honoured per layer; descs is a HOST array. */
+#define VB_ENCODER_ARENA_BUFFERS 14
+int64_t vb_encoder_arena_layout(int32_t batch, int32_t seq, int32_t hidden, int32_t heads, int32_t inter, int32_t attn_dropout_on,
+                                int64_t* offsets /* [VB_ENCODER_ARENA_BUFFERS] */);
+/* x_in bf16 [M, H]; the output of layer l is arena buffer 13 (y) of slot l. */
+int vb_encoder_fwd(const vb_layer_desc* descs, int32_t n_layers, const void* x_in, void* arena, void* stream);
+/* dy: gradient w.r.t. the LAST layer's output; dx: gradient w.r.t. x_in; grads: HOST array [n_layers]. */
+int vb_encoder_bwd(const vb_layer_desc* descs, int32_t n_layers, const void* x_in, void* arena, const void* dy, void* dx,
+                   const vb_layer_grads* grads, const vb_layer_scratch* scratch, void* stream);
+
 /* ---- BertEmbeddingsWithVisualEmbedding (M.py:1169-1257) ----------------------------------- */
 typedef struct {
     int32_t batch, text_len, num_regions, hidden, visual_dim, vocab, max_pos, n_types;

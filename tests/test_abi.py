@@ -26,15 +26,34 @@ def test_library_loads_and_exports_every_declared_symbol():
 def test_struct_mirrors_match_c_sizes(tmp_path):
     from visualbert_b200 import _lib
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "vbert_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %d\\n",'
+    src.write_text('#include <stdio.h>\n#include "vbert_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %d %d %d\\n",'
                    'sizeof(vb_gemm_args),sizeof(vb_layer_desc),sizeof(vb_layer_acts),sizeof(vb_layer_grads),'
-                   'sizeof(vb_layer_scratch),sizeof(vb_embed_desc),sizeof(vb_embed_acts),sizeof(vb_embed_grads),sizeof(vb_adam_tensor),VB_ADAM_CHUNK);return 0;}\n')
+                   'sizeof(vb_layer_scratch),sizeof(vb_embed_desc),sizeof(vb_embed_acts),sizeof(vb_embed_grads),sizeof(vb_adam_tensor),'
+                   'sizeof(vb_cast_item),VB_ADAM_CHUNK,VB_CAST_CHUNK,VB_ENCODER_ARENA_BUFFERS);return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     mirrors = [_lib.GemmArgs, _lib.LayerDesc, _lib.LayerActs, _lib.LayerGrads, _lib.LayerScratch, _lib.EmbedDesc,
-               _lib.EmbedActs, _lib.EmbedGrads, _lib.AdamTensor]
-    assert sizes == [ctypes.sizeof(m) for m in mirrors] + [_lib.VB_ADAM_CHUNK]
+               _lib.EmbedActs, _lib.EmbedGrads, _lib.AdamTensor, _lib.CastItem]
+    assert sizes == [ctypes.sizeof(m) for m in mirrors] + [_lib.VB_ADAM_CHUNK, _lib.VB_CAST_CHUNK, _lib.VB_ENCODER_ARENA_BUFFERS]
+    assert len(_lib.ARENA_NAMES) == _lib.VB_ENCODER_ARENA_BUFFERS
+
+
+def test_encoder_arena_layout_is_aligned_and_ordered():
+    """vb_encoder_arena_layout (no GPU needed): 14 buffers per layer slot, 256-byte aligned, sized for the shapes."""
+    from visualbert_b200 import _lib
+    L = _lib.lib()
+    off = (ctypes.c_int64 * _lib.VB_ENCODER_ARENA_BUFFERS)()
+    B, S, H, A, I = 4, 56, 768, 12, 3072
+    stride = L.vb_encoder_arena_layout(B, S, H, A, I, 1, off)
+    o = list(off)
+    M = B * S
+    assert o[0] == 0 and all(x % 256 == 0 for x in o) and stride % 256 == 0
+    sizes = dict(zip(_lib.ARENA_NAMES, [b - a for a, b in zip(o, o[1:] + [stride])]))
+    assert sizes["qkv"] >= M * 3 * H * 2 and sizes["u"] >= M * I * 2 and sizes["y"] >= M * H * 2 and sizes["lse"] >= B * A * S * 4
+    assert sizes["keep_mask"] >= L.vb_attention_keep_bytes(B, S, A)
+    stride0 = L.vb_encoder_arena_layout(B, S, H, A, I, 0, off)
+    assert stride0 == stride - sizes["keep_mask"]
 
 
 def test_argument_validation_reports_through_vb_last_error():

@@ -73,8 +73,10 @@ EXPORTS = [
     "vb_abi_version", "vb_last_error", "vb_launch_count", "vb_profile_enable", "vb_profile_read", "vb_gemm", "vb_layernorm_fwd", "vb_layernorm_bwd",
     "vb_attention_keep_bytes", "vb_attention_fwd", "vb_attention_bwd", "vb_mask_bias", "vb_cast_f32_to_bf16", "vb_cast_bf16_to_f32",
     "vb_colsum_bf16", "vb_cross_entropy_fwd", "vb_cross_entropy_bwd", "vb_layer_fwd", "vb_layer_bwd", "vb_embed_fwd", "vb_embed_bwd",
-    "vb_bert_adam_step", "vb_cast_multi",
+    "vb_bert_adam_step", "vb_cast_multi", "vb_encoder_arena_layout", "vb_encoder_fwd", "vb_encoder_bwd",
 ]
+VB_ENCODER_ARENA_BUFFERS = 14
+ARENA_NAMES = ("qkv", "ctx", "lse", "pre1", "mean1", "rstd1", "x1", "u", "g", "pre2", "mean2", "rstd2", "keep_mask", "y")
 
 
 class VBertLibraryError(RuntimeError):
@@ -97,6 +99,7 @@ def lib():
         h.vb_launch_count.restype = ctypes.c_int64
         h.vb_abi_version.restype = ctypes.c_int
         h.vb_attention_keep_bytes.restype = ctypes.c_int64
+        h.vb_encoder_arena_layout.restype = ctypes.c_int64
         _lib = h
     return _lib
 

@@ -127,6 +127,72 @@ int layer_bwd(const vb_layer_desc* d, const void* x_in, const vb_layer_acts* s, 
     return 0;
 }
 
+// ---- whole-encoder entry points: one arena, one call (see include/vbert_b200.h) ----
+static long long align256(long long x) { return (x + 255) / 256 * 256; }
+
+long long encoder_arena_layout(int B, int S, int H, int A, int I, int attn_drop, long long* off) {
+    const long long M = static_cast<long long>(B) * S;
+    const long long sizes[VB_ENCODER_ARENA_BUFFERS] = {
+        M * 3 * H * 2, M * H * 2, static_cast<long long>(B) * A * S * 4, M * H * 2, M * 4, M * 4, M * H * 2, M * I * 2, M * I * 2,
+        M * H * 2, M * 4, M * 4, attn_drop ? attn_keep_bytes(B, S, A) : 0, M * H * 2};
+    long long o = 0;
+    for (int i = 0; i < VB_ENCODER_ARENA_BUFFERS; ++i) {
+        if (off) off[i] = o;
+        o += align256(sizes[i]);
+    }
+    return o;
+}
+
+static void arena_acts(const vb_layer_desc* d, void* arena, int l, vb_layer_acts* a, void** y) {
+    long long off[VB_ENCODER_ARENA_BUFFERS];
+    const long long stride = encoder_arena_layout(d->batch, d->seq, d->hidden, d->heads, d->inter, d->attn_dropout > 0.f, off);
+    char* base = static_cast<char*>(arena) + l * stride;
+    a->qkv = base + off[0]; a->ctx = base + off[1]; a->lse = reinterpret_cast<float*>(base + off[2]);
+    a->pre1 = base + off[3]; a->mean1 = reinterpret_cast<float*>(base + off[4]); a->rstd1 = reinterpret_cast<float*>(base + off[5]);
+    a->x1 = base + off[6]; a->u = base + off[7]; a->g = base + off[8]; a->pre2 = base + off[9];
+    a->mean2 = reinterpret_cast<float*>(base + off[10]); a->rstd2 = reinterpret_cast<float*>(base + off[11]);
+    a->keep_mask = d->attn_dropout > 0.f ? base + off[12] : nullptr;
+    *y = base + off[13];
+}
+
+int encoder_fwd(const vb_layer_desc* descs, int n, const void* x_in, void* arena, cudaStream_t st) {
+    VB_REQUIRE(descs && n > 0 && x_in && arena, "encoder_fwd: null pointer / no layers");
+    const void* x = x_in;
+    for (int l = 0; l < n; ++l) {
+        VB_REQUIRE(descs[l].batch == descs[0].batch && descs[l].seq == descs[0].seq && descs[l].hidden == descs[0].hidden &&
+                   descs[l].heads == descs[0].heads && descs[l].inter == descs[0].inter &&
+                   (descs[l].attn_dropout > 0.f) == (descs[0].attn_dropout > 0.f), "encoder_fwd: layers differ in shape");
+        vb_layer_acts a;
+        void* y;
+        arena_acts(&descs[l], arena, l, &a, &y);
+        VB_TRY(layer_fwd(&descs[l], x, y, &a, st));
+        x = y;
+    }
+    return 0;
+}
+
+int encoder_bwd(const vb_layer_desc* descs, int n, const void* x_in, void* arena, const void* dy, void* dx,
+                const vb_layer_grads* grads, const vb_layer_scratch* w, cudaStream_t st) {
+    VB_REQUIRE(descs && n > 0 && x_in && arena && dy && dx && grads && w, "encoder_bwd: null pointer / no layers");
+    const void* g_in = dy;
+    for (int l = n - 1; l >= 0; --l) {
+        vb_layer_acts a;
+        void* y;
+        arena_acts(&descs[l], arena, l, &a, &y);
+        const void* xl = x_in;
+        if (l > 0) {
+            vb_layer_acts ap;
+            void* yp;
+            arena_acts(&descs[l - 1], arena, l - 1, &ap, &yp);
+            xl = yp;
+        }
+        // the gradient buffer ping-pongs inside `dx` (vb_layer_bwd allows dx to alias dy)
+        VB_TRY(layer_bwd(&descs[l], xl, &a, g_in, dx, &grads[l], w, st));
+        g_in = dx;
+    }
+    return 0;
+}
+
 static int check_embed(const vb_embed_desc* d) {
     VB_REQUIRE(d != nullptr, "embed: null descriptor");
     VB_REQUIRE(d->batch > 0 && d->text_len > 0 && d->num_regions >= 0, "embed: bad shape");
@@ -206,6 +272,20 @@ int vb_layer_fwd(const vb_layer_desc* d, const void* x_in, void* x_out, const vb
 int vb_layer_bwd(const vb_layer_desc* d, const void* x_in, const vb_layer_acts* acts, const void* dy, void* dx,
                  const vb_layer_grads* grads, const vb_layer_scratch* scratch, void* stream) {
     return vb::layer_bwd(d, x_in, acts, dy, dx, grads, scratch, static_cast<cudaStream_t>(stream));
+}
+int64_t vb_encoder_arena_layout(int32_t batch, int32_t seq, int32_t hidden, int32_t heads, int32_t inter, int32_t attn_dropout_on,
+                                int64_t* offsets) {
+    long long off[VB_ENCODER_ARENA_BUFFERS];
+    const long long stride = vb::encoder_arena_layout(batch, seq, hidden, heads, inter, attn_dropout_on, off);
+    if (offsets) for (int i = 0; i < VB_ENCODER_ARENA_BUFFERS; ++i) offsets[i] = off[i];
+    return stride;
+}
+int vb_encoder_fwd(const vb_layer_desc* descs, int32_t n_layers, const void* x_in, void* arena, void* stream) {
+    return vb::encoder_fwd(descs, n_layers, x_in, arena, static_cast<cudaStream_t>(stream));
+}
+int vb_encoder_bwd(const vb_layer_desc* descs, int32_t n_layers, const void* x_in, void* arena, const void* dy, void* dx,
+                   const vb_layer_grads* grads, const vb_layer_scratch* scratch, void* stream) {
+    return vb::encoder_bwd(descs, n_layers, x_in, arena, dy, dx, grads, scratch, static_cast<cudaStream_t>(stream));
 }
 int vb_embed_fwd(const vb_embed_desc* d, void* y, const vb_embed_acts* acts, void* stream) {
     return vb::embed_fwd_api(d, y, acts, static_cast<cudaStream_t>(stream));

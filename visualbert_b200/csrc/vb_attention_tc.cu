@@ -386,33 +386,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 }  // namespace
-
-// 3-D bf16 tensor map over x[B][S][ld]: box = 64 columns x box_rows rows x 1 batch, 128-byte swizzle, OOB rows -> 0
-int make_tmap_3d(CUtensorMap* m, const void* ptr, int S, int B, int ld, int box_rows) {
-    static EncodeTiledFn fn = nullptr;
-    if (fn == nullptr) {
-        void* sym = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(sym);
-    }
-    VB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled unavailable");
-    cuuint64_t dims[3] = {static_cast<cuuint64_t>(ld), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(B)};
-    cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(S) * ld * 2};
-    cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    VB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", static_cast<int>(r));
-    return 0;
-}
 
 bool attn_fwd_tc_supported(const AttnParams& p) {
     return p.S >= 1 && p.S <= kMaxNpad && (p.H * 3) % 8 == 0 && (reinterpret_cast<uintptr_t>(p.qkv) & 15) == 0;

@@ -654,23 +654,65 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+// Tensor-map cache: a training step encodes ~1000 descriptors (2 per GEMM, 3-4 per attention call), each a driver call of
+// 1-2 us on the launch path; with the activation arena of vb_encoder_fwd/bwd the same (pointer, shape) tuples recur every
+// step, so the encoded 128-byte maps are memoised per thread (no locks on the launch path; direct-mapped, 4096 slots).
+struct TmapKey {
+    const void* ptr; uint64_t d0, d1, d2, s0, s1; uint32_t b0, b1, b2, rank; int dev;
+    bool operator==(const TmapKey& o) const {
+        return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && s0 == o.s0 && s1 == o.s1 && b0 == o.b0 && b1 == o.b1 && b2 == o.b2 &&
+               rank == o.rank && dev == o.dev;
+    }
+};
+struct TmapSlot { TmapKey key; CUtensorMap map; bool used; };
+constexpr int kTmapSlots = 4096;
+static thread_local std::vector<TmapSlot>* g_tmap_cache = nullptr;
+
+static int encode_tmap_cached(CUtensorMap* m, const void* ptr, uint32_t rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                              const cuuint32_t* box) {
+    TmapKey k;
+    memset(&k, 0, sizeof(k));
+    k.ptr = ptr; k.rank = rank; k.dev = current_device();
+    k.d0 = dims[0]; k.d1 = dims[1]; k.d2 = rank > 2 ? dims[2] : 1;
+    k.s0 = strides[0]; k.s1 = rank > 2 ? strides[1] : 0;
+    k.b0 = box[0]; k.b1 = box[1]; k.b2 = rank > 2 ? box[2] : 1;
+    uint64_t h = reinterpret_cast<uintptr_t>(ptr) * 0x9E3779B97F4A7C15ull;
+    h ^= (k.d0 * 31 + k.d1) * 0xBF58476D1CE4E5B9ull + k.d2 * 1315423911ull + k.s0 * 2654435761ull + k.s1 * 40503ull;
+    h ^= (static_cast<uint64_t>(k.b1) << 20) ^ (static_cast<uint64_t>(k.b0) << 8) ^ k.b2 ^ (static_cast<uint64_t>(k.dev) << 40);
+    h ^= h >> 29;
+    if (g_tmap_cache == nullptr) { g_tmap_cache = new std::vector<TmapSlot>(kTmapSlots); for (auto& sl : *g_tmap_cache) sl.used = false; }
+    TmapSlot& sl = (*g_tmap_cache)[h & (kTmapSlots - 1)];
+    if (sl.used && sl.key == k) { *m = sl.map; return 0; }
+    EncodeTiledFn fn = get_encode_fn();
+    VB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled unavailable (driver too old / no GPU?)");
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (rank %u) failed with CUresult %d", rank, static_cast<int>(r));
+    sl.key = k; sl.map = *m; sl.used = true;
+    return 0;
+}
+
 // 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows of stride ld elements;
 // box = 64 x box_outer, 128-byte swizzle, out-of-bounds reads return zero.
 int make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld_elems,
                    uint32_t box_outer) {
-    EncodeTiledFn fn = get_encode_fn();
-    VB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled unavailable (driver too old / no GPU?)");
     VB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand not 16-byte aligned");
     VB_REQUIRE((ld_elems * 2) % 16 == 0, "TMA operand row stride must be a multiple of 8 elements");
     cuuint64_t dims[2] = {inner, outer};
     cuuint64_t strides[1] = {ld_elems * 2};
     cuuint32_t box[2] = {64, box_outer};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    VB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
-    return 0;
+    return encode_tmap_cached(m, ptr, 2, dims, strides, box);
+}
+
+// 3-D bf16 tensor map over x[B][S][ld]: box = 64 columns x box_rows rows x 1 batch, 128-byte swizzle, OOB rows -> 0
+int make_tmap_3d(CUtensorMap* m, const void* ptr, int S, int B, int ld, int box_rows) {
+    VB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * 2) % 16 == 0, "TMA operand (3-D) not 16-byte aligned");
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(ld), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(B)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(S) * ld * 2};
+    cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
+    return encode_tmap_cached(m, ptr, 3, dims, strides, box);
 }
 
 int current_device() {

@@ -16,6 +16,7 @@ int attn_fwd(const void* qkv, const float* mask_bias, void* ctx, float* lse, voi
 int attn_bwd(const void* qkv, const float* mask_bias, const void* ctx, const float* lse, const void* keep,
              const void* dctx, void* dqkv, float* drow, int B, int S, int A, int H, float dropout_p,
              unsigned long long seed, unsigned stream_id, cudaStream_t st);
+long long attn_keep_bytes(int B, int S, int A);
 int colsum(const void* x, long long ld, float* out, int M, int N, cudaStream_t st);
 int cast_f32_bf16(const float* src, void* dst, long long n, cudaStream_t st);
 int cast_bf16_f32(const void* src, float* dst, long long n, cudaStream_t st);

@@ -209,6 +209,25 @@ class BertEncoder(nn.Module):
         self.output_attention_weights = getattr(config, "output_attention_weights", False)
 
     def forward(self, hidden_states, attention_mask, output_all_encoded_layers=True, seed=0):
+        if attention_mask.dim() == 4:
+            attention_mask = attention_mask[:, 0, 0, :]
+        fused = (not self.output_attention_weights and hidden_states.is_cuda and len(self.layer) > 0
+                 and not (output_all_encoded_layers and torch.is_grad_enabled() and self.training)
+                 and os.environ.get("VB_ENCODER_FUSED", "1") != "0")
+        if fused:
+            # one C call for the whole stack (vb_encoder_fwd / vb_encoder_bwd, one activation arena)
+            l0 = self.layer[0]
+            train = self.training
+            plan = self.__dict__.get("_plan")
+            if plan is None:
+                plan = self.__dict__["_plan"] = ops.EncoderPlan()
+            meta = dict(heads=l0.attention.self.num_attention_heads, layer_index0=l0.layer_index,
+                        hidden_dropout=l0.hidden_dropout_prob if train else 0.0,
+                        attn_dropout=l0.attention_probs_dropout_prob if train else 0.0, seed=int(seed), train=train,
+                        caches=[l._weights for l in self.layer], plan=plan)
+            params = [p for l in self.layer for p in l._params()]
+            ys = ops.bert_encoder(hidden_states.to(torch.bfloat16), attention_mask.float().contiguous(), meta, params)
+            return list(ys) if output_all_encoded_layers else [ys[-1]]
         outs, attn = [], []
         for layer in self.layer:
             if self.output_attention_weights:

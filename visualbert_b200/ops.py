@@ -279,6 +279,128 @@ class _LayerFn(torch.autograd.Function):
                 dwi.view(I, H), dbi, dwout.view(H, I), dbout, dg2, db2)
 
 
+class EncoderPlan:
+    """Host-side state of the whole-encoder call (vb_encoder_fwd / vb_encoder_bwd): the ctypes descriptor and gradient
+    arrays are built once per (shape, weights) and only their per-step fields (seed, dropout) are touched afterwards."""
+
+    def __init__(self):
+        self.key = None
+
+    def prepare(self, caches, params, B, S, H, A, I, mbias, meta):
+        L = len(caches)
+        weights = [c.get(*[params[16 * l + i] for i in (0, 2, 4, 6, 10, 12, 1, 3, 5)], train=meta["train"]) for l, c in enumerate(caches)]
+        key = (B, S, H, A, I, L, tuple(w[0].data_ptr() for w in weights), tuple(p.data_ptr() for p in params), mbias.device)
+        if key != self.key:
+            self.descs = (_lib.LayerDesc * L)()
+            for l in range(L):
+                wqkv, wo, wi, wout, bqkv = weights[l]
+                qw, qb, kw, kb, vw, vb, ow, ob, g1, b1, iw, ib, dw, db, g2, b2 = params[16 * l: 16 * l + 16]
+                d = self.descs[l]
+                d.batch, d.seq, d.hidden, d.heads, d.inter = B, S, H, A, I
+                d.w_qkv, d.w_attn_out, d.w_inter, d.w_out = wqkv.data_ptr(), wo.data_ptr(), wi.data_ptr(), wout.data_ptr()
+                d.b_qkv, d.b_attn_out, d.ln1_gamma, d.ln1_beta = bqkv.data_ptr(), ob.data_ptr(), g1.data_ptr(), b1.data_ptr()
+                d.b_inter, d.b_out, d.ln2_gamma, d.ln2_beta = ib.data_ptr(), db.data_ptr(), g2.data_ptr(), b2.data_ptr()
+            self.key = key
+        for l in range(L):
+            d = self.descs[l]
+            d.hidden_dropout, d.attn_dropout, d.seed = meta["hidden_dropout"], meta["attn_dropout"], meta["seed"]
+            d.layer_index = meta["layer_index0"] + l
+            d.mask_bias = mbias.data_ptr()
+        off = (ctypes.c_int64 * _lib.VB_ENCODER_ARENA_BUFFERS)()
+        stride = int(_lib.lib().vb_encoder_arena_layout(B, S, H, A, I, 1 if meta["attn_dropout"] > 0 else 0, off))
+        return weights, stride, list(off)
+
+
+class _EncoderFn(torch.autograd.Function):
+    """BertEncoder (M.py:344-371): all layers in ONE vb_encoder_fwd / vb_encoder_bwd call over one activation arena."""
+
+    @staticmethod
+    def forward(ctx, x, mbias, meta, *params):
+        _require_cuda(x, "bert_encoder")
+        B, S, H = x.shape
+        L = len(params) // 16
+        I = params[10].shape[0]
+        A = meta["heads"]
+        x = x.contiguous()
+        with torch.cuda.device(x.device):
+            weights, stride, off = meta["plan"].prepare(meta["caches"], params, B, S, H, A, I, mbias, meta)
+            arena = torch.empty(L * stride, device=x.device, dtype=torch.uint8)
+            plan = meta["plan"]
+            _lib.check(_lib.lib().vb_encoder_fwd(plan.descs, L, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(arena.data_ptr()), _stream()),
+                       "vb_encoder_fwd")
+        n = B * S * H * 2
+        outs = tuple(arena[l * stride + off[13]: l * stride + off[13] + n].view(_BF16).view(B, S, H) for l in range(L))
+        ctx.meta, ctx.arena, ctx.params, ctx.weights = meta, arena, params, weights
+        ctx.shape = (B, S, H, A, I, L)
+        ctx.save_for_backward(x, mbias)
+        ctx.mark_non_differentiable(*outs[:-1])
+        return outs
+
+    @staticmethod
+    def backward(ctx, *douts):
+        x, mbias = ctx.saved_tensors
+        meta, params = ctx.meta, ctx.params
+        B, S, H, A, I, L = ctx.shape
+        M = B * S
+        dev = x.device
+        dy = douts[-1].to(_BF16).contiguous()
+        groups = []
+        for l in range(L):
+            qw, qb, kw, kb, vw, vb = params[16 * l: 16 * l + 6]
+            groups += [(qw, kw, vw), (qb, kb, vb)]
+        direct = _grad_targets(params, groups)
+        sizes = [3 * H * H, 3 * H, H * H, H, H, H, I * H, I, H * I, H, H, H]
+        grads = (_lib.LayerGrads * L)()
+        gnames = ("dw_qkv", "db_qkv", "dw_attn_out", "db_attn_out", "dln1_gamma", "dln1_beta",
+                  "dw_inter", "db_inter", "dw_out", "db_out", "dln2_gamma", "dln2_beta")
+        if direct is not None:
+            for l in range(L):
+                t = direct[16 * l: 16 * l + 16]
+                ptrs = (t[0], t[1], t[6], t[7], t[8], t[9], t[10], t[11], t[12], t[13], t[14], t[15])
+                for nme, tt in zip(gnames, ptrs):
+                    setattr(grads[l], nme, tt.data_ptr())
+            flat = None
+        else:
+            per = sum(sizes)
+            flat = torch.zeros(L * per, device=dev, dtype=torch.float32)
+            for l in range(L):
+                o = l * per
+                for nme, sz in zip(gnames, sizes):
+                    setattr(grads[l], nme, flat.data_ptr() + 4 * o)
+                    o += sz
+        hd = meta["hidden_dropout"] > 0
+        with torch.cuda.device(dev):
+            w = _scratch(dev, M, H, I, B, A, S, hd)
+            sc = _lib.LayerScratch(**{k: _ptr(t) for k, t in w.items()})
+            dx = torch.empty(B, S, H, device=dev, dtype=_BF16)
+            plan = meta["plan"]
+            for l in range(L):  # same step, same dropout streams as the forward
+                d = plan.descs[l]
+                d.hidden_dropout, d.attn_dropout, d.seed = meta["hidden_dropout"], meta["attn_dropout"], meta["seed"]
+                d.layer_index, d.mask_bias = meta["layer_index0"] + l, mbias.data_ptr()
+            _lib.check(_lib.lib().vb_encoder_bwd(plan.descs, L, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(ctx.arena.data_ptr()),
+                                                 ctypes.c_void_p(dy.data_ptr()), ctypes.c_void_p(dx.data_ptr()), grads, ctypes.byref(sc),
+                                                 _stream()), "vb_encoder_bwd")
+        ctx.arena = None
+        if direct is not None:
+            return (dx, None, None) + (None,) * (16 * L)
+        out = []
+        per = sum(sizes)
+        for l in range(L):
+            dwqkv, dbqkv, dwo, dbo, dg1, db1, dwi, dbi, dwout, dbout, dg2, db2 = torch.split(flat[l * per: (l + 1) * per], sizes)
+            dwq, dwk, dwv = dwqkv.view(3, H, H).unbind(0)
+            dbq, dbk, dbv = dbqkv.view(3, H).unbind(0)
+            out += [dwq, dbq, dwk, dbk, dwv, dbv, dwo.view(H, H), dbo, dg1, db1, dwi.view(I, H), dbi, dwout.view(H, I), dbout, dg2, db2]
+        return (dx, None, None) + tuple(out)
+
+
+def bert_encoder(x, mbias, meta, params):
+    """All layers at once. meta: dict(heads, layer_index0, hidden_dropout, attn_dropout, seed, train, caches=[LayerWeights],
+    plan=EncoderPlan); params: 16 tensors per layer in bert_layer order. Returns the tuple of all layer outputs (only
+    the last one is differentiable: a caller that needs gradients through intermediate outputs uses bert_layer)."""
+    return _EncoderFn.apply(x, mbias, meta, *params)
+
+
 def bert_layer(x, mbias, meta, params):
     """params: the 16 tensors of one BertLayer in reference order (q.w, q.b, k.w, k.b, v.w, v.b, attention.output
     dense.w/.b, LayerNorm.w/.b, intermediate.dense.w/.b, output.dense.w/.b, LayerNorm.w/.b)."""
