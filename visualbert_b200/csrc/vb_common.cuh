@@ -422,6 +422,21 @@ __device__ __forceinline__ void tmem_st_32x32b_x4(uint32_t taddr, uint32_t a, ui
 __device__ __forceinline__ void tmem_st_wait() {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
+// One lane of a CONVERGED warp (elect.sync). The MMA-issuing role runs its loop with all 32 lanes converged and predicates
+// only the tcgen05 instructions on this: the compiler then keeps descriptors and loop state in uniform registers. Guarding
+// the whole role with `if (lane == 0)` instead makes the code divergent, and every tcgen05.mma gets wrapped in an
+// ELECT / BRA.U.ANY serialisation loop (~100+ cycles of issue latency per MMA — measured in the attention kernels).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "elect.sync _|P1, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 // Register re-distribution between warp roles (whole warpgroups of 4 warps): the control warpgroup shrinks its
 // allocation, the element-wise warpgroups grow theirs; ptxas compiles the code that follows against the new limit.
 template <int N>

@@ -47,7 +47,8 @@ def _scratch(dev, M, H, I, B, A, S, need_drop):
             d_x1=torch.empty(M, H, device=dev, dtype=_BF16),
             d_ctx=torch.empty(M, H, device=dev, dtype=_BF16),
             drow=torch.empty(B, A, S, device=dev, dtype=torch.float32))
-        _scratch_cache.clear()  # keep a single shape resident
+        for k in [k for k in _scratch_cache if k[0] == dev]:   # keep a single shape resident PER DEVICE
+            del _scratch_cache[k]
         _scratch_cache[key] = w
     if need_drop and w["d_pre_drop"] is None:
         w["d_pre_drop"] = torch.empty(M, H, device=dev, dtype=_BF16)
@@ -60,8 +61,9 @@ def cast_to_bf16(src, out=None):
     src = src.contiguous()
     if out is None:
         out = torch.empty(src.shape, device=src.device, dtype=_BF16)
-    _lib.check(_lib.lib().vb_cast_f32_to_bf16(ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(out.data_ptr()),
-                                              ctypes.c_int64(src.numel()), _stream()), "vb_cast_f32_to_bf16")
+    with torch.cuda.device(src.device):   # the library launches on the CURRENT device's stream: make it the tensor's
+        _lib.check(_lib.lib().vb_cast_f32_to_bf16(ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                                  ctypes.c_int64(src.numel()), _stream()), "vb_cast_f32_to_bf16")
     return out
 
 
@@ -73,8 +75,9 @@ def mask_bias(input_mask, image_mask):
     im = input_mask.to(torch.int64).contiguous()
     vm = None if image_mask is None else image_mask.to(torch.int64).contiguous()
     out = torch.empty(B, T + V, device=input_mask.device, dtype=torch.float32)
-    _lib.check(_lib.lib().vb_mask_bias(ctypes.c_void_p(im.data_ptr()), ctypes.c_void_p(_ptr(vm)),
-                                       ctypes.c_void_p(out.data_ptr()), B, T, V, _stream()), "vb_mask_bias")
+    with torch.cuda.device(input_mask.device):
+        _lib.check(_lib.lib().vb_mask_bias(ctypes.c_void_p(im.data_ptr()), ctypes.c_void_p(_ptr(vm)),
+                                           ctypes.c_void_p(out.data_ptr()), B, T, V, _stream()), "vb_mask_bias")
     return out
 
 
@@ -220,8 +223,9 @@ class _LayerFn(torch.autograd.Function):
             b_inter=ib.data_ptr(), b_out=db.data_ptr(), ln2_gamma=g2.data_ptr(), ln2_beta=b2.data_ptr(),
             mask_bias=mbias.data_ptr())
         a = _lib.LayerActs(**{k: _ptr(t) for k, t in acts.items()})
-        _lib.check(_lib.lib().vb_layer_fwd(ctypes.byref(d), ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(y.data_ptr()),
-                                           ctypes.byref(a), _stream()), "vb_layer_fwd")
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().vb_layer_fwd(ctypes.byref(d), ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(y.data_ptr()),
+                                               ctypes.byref(a), _stream()), "vb_layer_fwd")
         ctx.meta = meta
         ctx.acts = acts
         ctx.params = (qw, qb, kw, kb, vw, vb, ow, ob, g1, b1, iw, ib, dw, db, g2, b2)
@@ -266,9 +270,10 @@ class _LayerFn(torch.autograd.Function):
             mask_bias=mbias.data_ptr())
         a = _lib.LayerActs(**{k: _ptr(t) for k, t in acts.items()})
         dx = torch.empty(B, S, H, device=dev, dtype=_BF16)
-        _lib.check(_lib.lib().vb_layer_bwd(ctypes.byref(d), ctypes.c_void_p(x.data_ptr()), ctypes.byref(a),
-                                           ctypes.c_void_p(dy.data_ptr()), ctypes.c_void_p(dx.data_ptr()),
-                                           ctypes.byref(g), ctypes.byref(sc), _stream()), "vb_layer_bwd")
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().vb_layer_bwd(ctypes.byref(d), ctypes.c_void_p(x.data_ptr()), ctypes.byref(a),
+                                               ctypes.c_void_p(dy.data_ptr()), ctypes.c_void_p(dx.data_ptr()),
+                                               ctypes.byref(g), ctypes.byref(sc), _stream()), "vb_layer_bwd")
         ctx.acts = None
         if direct is not None:
             return (dx, None, None) + (None,) * 16
@@ -460,8 +465,9 @@ class _EmbedFn(torch.autograd.Function):
             pos_vis=pos_vis.data_ptr(), type_vis=typ_vis.data_ptr(), gamma=gamma.data_ptr(), beta=beta.data_ptr(),
             visual_addend=_ptr(xb))
         a = _lib.EmbedActs(vis_proj=_ptr(vis_proj), pre=pre.data_ptr(), mean=mean.data_ptr(), rstd=rstd.data_ptr())
-        _lib.check(_lib.lib().vb_embed_fwd(ctypes.byref(d), ctypes.c_void_p(y.data_ptr()), ctypes.byref(a), _stream()),
-                   "vb_embed_fwd")
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().vb_embed_fwd(ctypes.byref(d), ctypes.c_void_p(y.data_ptr()), ctypes.byref(a), _stream()),
+                       "vb_embed_fwd")
         ctx.meta = meta
         ctx.shape = (B, T, V, H, Dv)
         ctx.feats_need_grad = feats is not None and feats.requires_grad
@@ -511,8 +517,9 @@ class _EmbedFn(torch.autograd.Function):
             dword=dword.data_ptr(), dpos=dpos.data_ptr(), dtype=dtyp.data_ptr(), dpos_vis=dpos_vis.data_ptr(),
             dtype_vis=dtyp_vis.data_ptr(), dw_proj=_ptr(dpw), db_proj=_ptr(dpb), dgamma=dgamma.data_ptr(),
             dbeta=dbeta.data_ptr(), d_pre=d_pre.data_ptr(), d_vis=_ptr(d_vis), d_feats=_ptr(d_feats))
-        _lib.check(_lib.lib().vb_embed_bwd(ctypes.byref(d), ctypes.byref(a), ctypes.c_void_p(dy.data_ptr()),
-                                           ctypes.byref(g), _stream()), "vb_embed_bwd")
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().vb_embed_bwd(ctypes.byref(d), ctypes.byref(a), ctypes.c_void_p(dy.data_ptr()),
+                                               ctypes.byref(g), _stream()), "vb_embed_bwd")
         dfe = None
         if d_feats is not None:
             dfe = d_feats.view(ctx.feats_shape).to(ctx.feats_dtype)
@@ -533,11 +540,12 @@ def bert_embeddings(meta, input_ids, token_type_ids, visual_type, feats, word, p
 # --------------------------------------------------------------------------------------------
 # masked-LM head on the library's kernels: decoder GEMMs on tcgen05, fused cross-entropy
 # --------------------------------------------------------------------------------------------
-def _gemm(**kw):
+def _gemm(dev, **kw):
     a = _lib.GemmArgs()
     for k, v in kw.items():
         setattr(a, k, v)
-    _lib.check(_lib.lib().vb_gemm(ctypes.byref(a), _stream()), "vb_gemm")
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().vb_gemm(ctypes.byref(a), _stream()), "vb_gemm")
 
 
 class DecoderWeights:
@@ -591,7 +599,7 @@ class _MlmDecoderFn(torch.autograd.Function):
         table, bias_p = cache.get(E, bias, train=train)
         t = t.to(_BF16).contiguous()
         logits = torch.empty(n, Vp, device=t.device, dtype=_BF16)
-        _gemm(A=t.data_ptr(), lda=H, B=table.data_ptr(), ldb=H, M=n, N=Vp, K=H, D=logits.data_ptr(), ldd=Vp,
+        _gemm(t.device, A=t.data_ptr(), lda=H, B=table.data_ptr(), ldb=H, M=n, N=Vp, K=H, D=logits.data_ptr(), ldd=Vp,
               bias=bias_p.data_ptr())
         ctx.save_for_backward(t, table)
         ctx.E, ctx.bias, ctx.V = E, bias, V
@@ -605,7 +613,7 @@ class _MlmDecoderFn(torch.autograd.Function):
         Vp = dlogits.shape[1]
         dlogits = dlogits.contiguous()
         dt = torch.empty(n, H, device=t.device, dtype=_BF16)
-        _gemm(A=dlogits.data_ptr(), lda=Vp, B=table.data_ptr(), ldb=H, b_mn_major=1, M=n, N=H, K=Vp, D=dt.data_ptr(), ldd=H)
+        _gemm(t.device, A=dlogits.data_ptr(), lda=Vp, B=table.data_ptr(), ldb=H, b_mn_major=1, M=n, N=H, K=Vp, D=dt.data_ptr(), ldd=H)
         direct = _grad_targets((E, bias))
         if direct is not None:
             dE, db = direct
@@ -613,10 +621,11 @@ class _MlmDecoderFn(torch.autograd.Function):
         else:
             dE = torch.zeros(V, H, device=t.device, dtype=torch.float32)
             db_pad = torch.zeros(Vp, device=t.device, dtype=torch.float32)
-        _gemm(A=dlogits.data_ptr(), lda=Vp, a_mn_major=1, B=t.data_ptr(), ldb=H, b_mn_major=1, M=V, N=H, K=n,
+        _gemm(t.device, A=dlogits.data_ptr(), lda=Vp, a_mn_major=1, B=t.data_ptr(), ldb=H, b_mn_major=1, M=V, N=H, K=n,
               D=dE.data_ptr(), ldd=H, d_fp32=1, splits=1)
-        _lib.check(_lib.lib().vb_colsum_bf16(ctypes.c_void_p(dlogits.data_ptr()), ctypes.c_int64(Vp), ctypes.c_void_p(db_pad.data_ptr()),
-                                             n, Vp, _stream()), "vb_colsum_bf16")
+        with torch.cuda.device(t.device):
+            _lib.check(_lib.lib().vb_colsum_bf16(ctypes.c_void_p(dlogits.data_ptr()), ctypes.c_int64(Vp), ctypes.c_void_p(db_pad.data_ptr()),
+                                                 n, Vp, _stream()), "vb_colsum_bf16")
         if direct is not None:
             db.add_(db_pad[:V])
             return dt, None, None, None, None
@@ -637,9 +646,10 @@ class _CrossEntropyFn(torch.autograd.Function):
         labels = labels.to(torch.int64).contiguous()
         lse = torch.empty(n, device=logits.device, dtype=torch.float32)
         rows = torch.empty(n, device=logits.device, dtype=torch.float32)
-        _lib.check(_lib.lib().vb_cross_entropy_fwd(ctypes.c_void_p(logits.data_ptr()), ctypes.c_int64(Vp),
-                                                   ctypes.c_void_p(labels.data_ptr()), n, V, ctypes.c_void_p(lse.data_ptr()),
-                                                   ctypes.c_void_p(rows.data_ptr()), _stream()), "vb_cross_entropy_fwd")
+        with torch.cuda.device(logits.device):
+            _lib.check(_lib.lib().vb_cross_entropy_fwd(ctypes.c_void_p(logits.data_ptr()), ctypes.c_int64(Vp),
+                                                       ctypes.c_void_p(labels.data_ptr()), n, V, ctypes.c_void_p(lse.data_ptr()),
+                                                       ctypes.c_void_p(rows.data_ptr()), _stream()), "vb_cross_entropy_fwd")
         ctx.logits, ctx.labels, ctx.lse, ctx.V = logits, labels, lse, V
         return rows.mean()
 
@@ -648,9 +658,10 @@ class _CrossEntropyFn(torch.autograd.Function):
         logits, labels, lse, V = ctx.logits, ctx.labels, ctx.lse, ctx.V
         n, Vp = logits.shape
         scale = (g.float() / n).reshape(1).contiguous()
-        _lib.check(_lib.lib().vb_cross_entropy_bwd(ctypes.c_void_p(logits.data_ptr()), ctypes.c_int64(Vp),
-                                                   ctypes.c_void_p(labels.data_ptr()), n, V, Vp, ctypes.c_void_p(lse.data_ptr()),
-                                                   ctypes.c_void_p(scale.data_ptr()), _stream()), "vb_cross_entropy_bwd")
+        with torch.cuda.device(logits.device):
+            _lib.check(_lib.lib().vb_cross_entropy_bwd(ctypes.c_void_p(logits.data_ptr()), ctypes.c_int64(Vp),
+                                                       ctypes.c_void_p(labels.data_ptr()), n, V, Vp, ctypes.c_void_p(lse.data_ptr()),
+                                                       ctypes.c_void_p(scale.data_ptr()), _stream()), "vb_cross_entropy_bwd")
         ctx.logits = None
         return logits, None, None
 
