@@ -11,7 +11,7 @@ seg = launches[marks[-2]:marks[-1]]
 
 
 def family(n):
-    n = n.replace("void ", "").replace("vb::", "")
+    n = n.replace("void ", "").replace("vb::", "").replace("<unnamed>::", "")
     m = re.match(r"(gemm_tcgen05(?:_2cta)?_kernel)<(\d), (\d), (\d+)(?:, (\d))?>", n)
     if m:
         a, b = m.group(2), m.group(3)

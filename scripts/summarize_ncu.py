@@ -35,10 +35,10 @@ def to_us(v, unit):
 
 
 # order of the library's launches in one layer fwd+bwd (vb_api.cu layer_fwd / layer_bwd)
-LABELS = ["fwd qkv GEMM", "fwd attention dropout mask", "fwd attention", "fwd attn-out GEMM (+bias+dropout+residual)", "fwd LN1", "fwd FFN-up GEMM (+bias+GELU, 2 stores)",
+LABELS = ["fwd qkv GEMM", "fwd attention dropout mask (+transpose)", "fwd attention (tcgen05)", "fwd attn-out GEMM (+bias+dropout+residual)", "fwd LN1", "fwd FFN-up GEMM (+bias+GELU, 2 stores)",
           "fwd FFN-down GEMM (+bias+dropout+residual)", "fwd LN2", "bwd LN2", "bwd FFN-down wgrad", "bwd FFN-down dgrad (*gelu')",
           "bwd colsum (b_inter)", "bwd FFN-up wgrad", "bwd FFN-up dgrad (+addend)", "bwd LN1", "bwd attn-out wgrad", "bwd attn-out dgrad",
-          "bwd attention delta", "bwd attention dQ/dK/dV (P, dS in smem)", "bwd colsum (b_qkv)", "bwd qkv wgrad", "bwd qkv dgrad (+addend)"]
+          "bwd attention delta", "bwd attention dQ/dK/dV (tcgen05)", "bwd colsum (b_qkv)", "bwd qkv wgrad", "bwd qkv dgrad (+addend)"]
 lines = ["| # | launch | kernel | µs | DRAM rd MB | DRAM wr MB | DRAM % | tensor % | IPC | regs | grid×block |", "|---|---|---|---|---|---|---|---|---|---|---|"]
 gemm_traffic, gemm_t, tot = [], [], 0.0
 for i, r in enumerate(data):

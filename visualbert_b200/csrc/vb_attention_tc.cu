@@ -167,8 +167,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ---------------- MMA issuer ----------------
+        {
+            // ---------------- MMA issuer: the whole warp runs the loop converged, one elected lane issues ----------------
             const uint32_t idesc_qk = idesc_bf16(kQRows, npad, false, false);
             const uint32_t idesc_pv = idesc_bf16(kQRows, kHd, false, true);
             auto issue_s = [&](int n) {
@@ -178,20 +178,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 tcgen05_fence_after();
                 // tile 0: the 128-row Q tile; tile 1: the compact window, addressed `offset` rows before its start
                 const uint32_t qa = t == 0 ? q_tile(s) : q2_win(s) - static_cast<uint32_t>(tile2_offset(li, tp.r2pad) * 128);
+                const UmmaDesc dq = make_umma_desc_sw128(qa, 0, 1024), dk = make_umma_desc_sw128(k_tile(s), 0, 1024);
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < kHd / 16; ++k) {
-                    const uint64_t ad = smem_desc_sw128(qa + k * 32, 0, 1024);
-                    const uint64_t bd = smem_desc_sw128(k_tile(s) + k * 32, 0, 1024);
-                    umma_bf16(tmem_s(bf), ad, bd, idesc_qk, k > 0 ? 1u : 0u);
+                    for (int k = 0; k < kHd / 16; ++k) umma_bf16(tmem_s(bf), dq.at(k * 32), dk.at(k * 32), idesc_qk, k > 0 ? 1u : 0u);
+                    umma_commit(bar(SFULL0 + bf));
                 }
-                umma_commit(bar(SFULL0 + bf));
-                if (tp.dbg != nullptr && blockIdx.x == 0 && n < 32) tp.dbg[n * 16 + 12] = clock64();
+                __syncwarp();
+                if (tp.dbg != nullptr && blockIdx.x == 0 && n < 32 && lane == 0) tp.dbg[n * 16 + 12] = clock64();
             };
             auto issue_pv = [&](int n) {
                 const int li = n / nq, t = n - li * nq;
                 const int s = li % kStagesTc, bf = n & 1;
                 const uint32_t ph = (n >> 1) & 1;
-                const bool stamp = tp.dbg != nullptr && blockIdx.x == 0 && n < 32;
+                const bool stamp = tp.dbg != nullptr && blockIdx.x == 0 && n < 32 && lane == 0;
                 if (stamp) tp.dbg[n * 16 + 8] = clock64();
                 mbar_wait(bar(PFULL0 + bf), ph);
                 if (stamp) tp.dbg[n * 16 + 9] = clock64();
@@ -199,13 +199,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 tcgen05_fence_after();
                 if (stamp) tp.dbg[n * 16 + 10] = clock64();
                 const int ksteps = npad / 16;
-                for (int k = 0; k < ksteps; ++k) {
+                const UmmaDesc dv = make_umma_desc_sw128(v_tile(s), 0, 1024);
+                if (elect_one()) {
                     // A = P: bf16 in TMEM, 16 keys = 8 columns; B = V: MN-major [keys x 128 B], 16 key rows per step
-                    const uint64_t bd = smem_desc_sw128(v_tile(s) + k * 2048, 0, 1024);
-                    umma_bf16_ts(tmem_o(bf), tmem_s(bf) + k * 8, bd, idesc_pv, k > 0 ? 1u : 0u);
+                    for (int k = 0; k < ksteps; ++k) umma_bf16_ts(tmem_o(bf), tmem_s(bf) + k * 8, dv.at(k * 2048), idesc_pv, k > 0 ? 1u : 0u);
+                    umma_commit(bar(OFULL0 + bf));
+                    if (t == nq - 1) umma_commit(bar(EMPTY0 + s));  // every MMA of the item has retired: Q / K / V are free
                 }
-                umma_commit(bar(OFULL0 + bf));
-                if (t == nq - 1) umma_commit(bar(EMPTY0 + s));  // every MMA of the item has retired: Q / K / V are free
+                __syncwarp();
                 if (stamp) tp.dbg[n * 16 + 11] = clock64();
             };
             if (n_tiles > 0) issue_s(0);
