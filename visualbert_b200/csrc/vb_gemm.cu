@@ -269,14 +269,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int num_tiles = m_blocks * n_blocks * p.splits;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ---------------- TMA producer ----------------
+        {
+            // ---------------- TMA producer (converged warp, one elected lane issues) ----------------
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 const TileCoord tc = decode_tile(t, n_blocks, p.splits, k_blocks);
                 for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
+                    if (elect_one()) {
                     mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
                     if constexpr (!A_MN) {
                         tma_load_2d(a_tile(stage), &tmA, full_bar(stage), kb * BLOCK_K, tc.m_blk * BLOCK_M);
@@ -294,13 +295,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             tma_load_2d(b_tile(stage) + i * kAtomBytes, &tmB, full_bar(stage),
                                         tc.n_blk * BLOCK_N + i * 64, kb * BLOCK_K);
                     }
+                    }
+                    __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ---------------- MMA issuer ----------------
+        {
+            // ---------------- MMA issuer: the warp runs the loop converged, one elected lane issues (uniform-register
+            // descriptors, back-to-back UTCHMMA; see profiles/r02_attention_tc.md §2) ----------------
             constexpr uint32_t idesc = make_idesc(BLOCK_N, A_MN, B_MN);
             // K-major: advance 16 elements (32 B) inside the swizzle row; MN-major: 16 k-rows (2 KB)
             constexpr uint32_t a_kstep = A_MN ? UMMA_K * 128 : UMMA_K * 2;
@@ -320,14 +324,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tcgen05_fence_after();
+                    const UmmaDesc ad = make_umma_desc_sw128(a_tile(stage), a_lbo, 1024), bd = make_umma_desc_sw128(b_tile(stage), b_lbo, 1024);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        const uint64_t ad = make_smem_desc(a_tile(stage) + k * a_kstep, a_lbo, 1024);
-                        const uint64_t bd = make_smem_desc(b_tile(stage) + k * b_kstep, b_lbo, 1024);
-                        umma_bf16(d_tmem, ad, bd, idesc, (kb > tc.kb_begin || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                            umma_bf16(d_tmem, ad.at(k * a_kstep), bd.at(k * b_kstep), idesc, (kb > tc.kb_begin || k > 0) ? 1u : 0u);
+                        umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+                        if (kb == tc.kb_end - 1) umma_commit(tfull_bar(acc));
                     }
-                    umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
-                    if (kb == tc.kb_end - 1) umma_commit(tfull_bar(acc));
+                    __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -493,8 +498,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ---------------- TMA producer (both CTAs) ----------------
+        {
+            // ---------------- TMA producer (both CTAs; converged warp, one elected lane issues) ----------------
             int stage = 0;
             uint32_t phase = 0;
             for (int t = cluster_id; t < num_tiles; t += num_clusters) {
@@ -503,6 +508,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 const int n0 = tc.n_blk * BLOCK_N + static_cast<int>(rank) * 128;
                 for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
+                    if (elect_one()) {
                     if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
                     else mbar_arrive_remote(full_bar(stage), 0);
                     if constexpr (!A_MN) {
@@ -519,13 +525,15 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                         for (int i = 0; i < 2; ++i)
                             tma_load_2d_2cta(b_tile(stage) + i * kAtomBytes, &tmB, full_bar(stage), n0 + i * 64, kb * BLOCK_K);
                     }
+                    }
+                    __syncwarp();
                     if (++stage == kStages2) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && leader) {
-            // ---------------- MMA issuer (leader CTA only) ----------------
+        if (leader) {
+            // ---------------- MMA issuer (leader CTA only): converged warp, one elected lane issues ----------------
             constexpr uint32_t idesc = make_idesc_m(256, BLOCK_N, A_MN, B_MN);
             constexpr uint32_t a_kstep = A_MN ? UMMA_K * 128 : UMMA_K * 2;
             constexpr uint32_t b_kstep = B_MN ? UMMA_K * 128 : UMMA_K * 2;
@@ -544,14 +552,15 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tcgen05_fence_after();
+                    const UmmaDesc ad = make_umma_desc_sw128(a_tile(stage), a_lbo, 1024), bd = make_umma_desc_sw128(b_tile(stage), b_lbo, 1024);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        const uint64_t ad = make_smem_desc(a_tile(stage) + k * a_kstep, a_lbo, 1024);
-                        const uint64_t bd = make_smem_desc(b_tile(stage) + k * b_kstep, b_lbo, 1024);
-                        umma_bf16_2cta(d_tmem, ad, bd, idesc, (kb > tc.kb_begin || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                            umma_bf16_2cta(d_tmem, ad.at(k * a_kstep), bd.at(k * b_kstep), idesc, (kb > tc.kb_begin || k > 0) ? 1u : 0u);
+                        umma_commit_2cta(empty_bar(stage));
+                        if (kb == tc.kb_end - 1) umma_commit_2cta(tfull_bar(acc));
                     }
-                    umma_commit_2cta(empty_bar(stage));
-                    if (kb == tc.kb_end - 1) umma_commit_2cta(tfull_bar(acc));
+                    __syncwarp();
                     if (++stage == kStages2) { stage = 0; phase ^= 1u; }
                 }
             }
