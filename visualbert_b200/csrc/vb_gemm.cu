@@ -163,7 +163,12 @@ __device__ __forceinline__ void store16_bf16(bf16* p, const float (&f)[16]) {
 // `sbias` points at the 16 staged bias values of these columns in shared memory (or nullptr).
 // `ex` holds the 16 bf16 of the residual (addend) or of gelu'(u) (aux_in) for these columns, prefetched by the
 // caller one chunk ahead so the row-strided global load never sits on the critical path.
-template <bool OUT_F32>
+// EPI selects the epilogue at COMPILE time for the CTA-pair kernel: the generic form (every option a run-time branch, all 8 chunks
+// unrolled) compiled to ~6 000 instructions (95 KB) per kernel — three times the SM's 32 KB L1.5 instruction cache, with
+// `no_instruction` stalls of 0.5-2.4 warps per issue cycle on the epilogue-bound launches. A specialised kernel carries only its path.
+enum { EPI_GENERIC = 0, EPI_BIAS = 1, EPI_RESID = 2, EPI_DROP_RESID = 3, EPI_GELU_FWD = 4, EPI_DGELU_BWD = 5 };
+
+template <bool OUT_F32, int EPI = EPI_GENERIC>
 __device__ __forceinline__ void epilogue16(const GemmParams& p, int row, int col, const float* sbias, const uint32_t (&ex)[8],
                                            float (&x)[16]) {
     if (sbias != nullptr) {
@@ -178,7 +183,8 @@ __device__ __forceinline__ void epilogue16(const GemmParams& p, int row, int col
 #pragma unroll
         for (int i = 0; i < 4; ++i) red_add_v4_f32(d + 4 * i, x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
     } else {
-        if (p.drop_scale != 0.0f) {
+        constexpr bool kGeneric = EPI == EPI_GENERIC;
+        if (EPI == EPI_DROP_RESID || (kGeneric && p.drop_scale != 0.0f)) {
             const unsigned long long e8 =
                 (static_cast<unsigned long long>(row) * static_cast<unsigned>(p.N) + col) >> 3;
 #pragma unroll
@@ -188,7 +194,7 @@ __device__ __forceinline__ void epilogue16(const GemmParams& p, int row, int col
                 for (int i = 0; i < 8; ++i) x[8 * h + i] = ((keep >> i) & 1u) ? x[8 * h + i] * p.drop_scale : 0.0f;
             }
         }
-        if (p.addend != nullptr) {
+        if (EPI == EPI_RESID || EPI == EPI_DROP_RESID || (kGeneric && p.addend != nullptr)) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float2 t = unpack_bf16x2(ex[i]);
@@ -197,17 +203,17 @@ __device__ __forceinline__ void epilogue16(const GemmParams& p, int row, int col
             }
         }
         bf16* d = reinterpret_cast<bf16*>(p.D) + static_cast<long long>(row) * p.ldd + col;
-        if (p.epilogue == VB_EPI_GELU) {
+        if (EPI == EPI_GELU_FWD || (kGeneric && p.epilogue == VB_EPI_GELU)) {
             // aux_out <- gelu(u) (operand of the next GEMM), D <- gelu'(u) (all the backward needs of u)
             float gp[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) gelu_fwd_bwd(x[i], x[i], gp[i]);
             store16_bf16(d, gp);
             d = p.aux_out + static_cast<long long>(row) * p.ld_aux + col;
-        } else if (p.epilogue == 3) {  // debug/tuning only: two stores, no GELU math
+        } else if (kGeneric && p.epilogue == 3) {  // debug/tuning only: two stores, no GELU math
             store16_bf16(d, x);
             d = p.aux_out + static_cast<long long>(row) * p.ld_aux + col;
-        } else if (p.epilogue == VB_EPI_DGELU) {
+        } else if (EPI == EPI_DGELU_BWD || (kGeneric && p.epilogue == VB_EPI_DGELU)) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float2 t = unpack_bf16x2(ex[i]);
@@ -445,7 +451,7 @@ __host__ __device__ constexpr uint32_t make_idesc_m(int m, int n, bool a_mn, boo
            (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-template <bool A_MN, bool B_MN, bool OUT_F32>
+template <bool A_MN, bool B_MN, bool OUT_F32, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmParams p) {
@@ -600,8 +606,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             uint32_t ex[kExAhead][8];
             const bf16* exp_ = nullptr;
             if constexpr (!OUT_F32) {
-                if (p.addend != nullptr) exp_ = p.addend + static_cast<long long>(row) * p.ld_add;
-                else if (p.epilogue == VB_EPI_DGELU) exp_ = p.aux_in + static_cast<long long>(row) * p.ld_aux;
+                constexpr bool kWantAdd = EPI == EPI_RESID || EPI == EPI_DROP_RESID;
+                if (kWantAdd || (EPI == EPI_GENERIC && p.addend != nullptr)) exp_ = p.addend + static_cast<long long>(row) * p.ld_add;
+                else if (EPI == EPI_DGELU_BWD || (EPI == EPI_GENERIC && p.epilogue == VB_EPI_DGELU)) exp_ = p.aux_in + static_cast<long long>(row) * p.ld_aux;
                 if (row >= p.M) exp_ = nullptr;
             }
 #pragma unroll
@@ -612,20 +619,26 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + half * (BLOCK_N / 2);
             uint32_t v[2][16];
             tmem_ld_32x32b_x16(taddr0, v[0]);
+            // chunks in groups of kExAhead: inside a group every buffer index is static; the group loop is NOT unrolled (code size)
+            static_assert(NCH % kExAhead == 0, "chunk groups");
+#pragma unroll 1
+            for (int k0 = 0; k0 < NCH; k0 += kExAhead) {
 #pragma unroll
-            for (int k = 0; k < NCH; ++k) {
-                tmem_ld_wait();
-                if (k + 1 < NCH) tmem_ld_32x32b_x16(taddr0 + (k + 1) * 16, v[(k + 1) & 1]);
-                const int col = col0 + k * 16;
-                if (row < p.M && col < p.N) {
-                    float x[16];
+                for (int kk = 0; kk < kExAhead; ++kk) {
+                    const int k = k0 + kk;
+                    tmem_ld_wait();
+                    if (k + 1 < NCH) tmem_ld_32x32b_x16(taddr0 + (k + 1) * 16, v[(kk + 1) & 1]);
+                    const int col = col0 + k * 16;
+                    if (row < p.M && col < p.N) {
+                        float x[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[k & 1][i]);
-                    epilogue16<OUT_F32>(p, row, col, has_bias ? sb + half * (BLOCK_N / 2) + k * 16 : nullptr, ex[k % kExAhead], x);
+                        for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[kk & 1][i]);
+                        epilogue16<OUT_F32, EPI>(p, row, col, has_bias ? sb + half * (BLOCK_N / 2) + k * 16 : nullptr, ex[kk], x);
+                    }
+                    // buffer kk is free again: refill it with the operand of chunk k + kExAhead
+                    if (k + kExAhead < NCH && exp_ != nullptr && col0 + (k + kExAhead) * 16 < p.N)
+                        ldg_v8(exp_ + col0 + (k + kExAhead) * 16, ex[kk]);
                 }
-                // buffer k % kExAhead is free again: refill it with the operand of chunk k + kExAhead
-                if (k + kExAhead < NCH && exp_ != nullptr && col0 + (k + kExAhead) * 16 < p.N)
-                    ldg_v8(exp_ + col0 + (k + kExAhead) * 16, ex[k % kExAhead]);
             }
             tcgen05_fence_before();
             if (leader) mbar_arrive(tempty_bar(acc));
@@ -759,9 +772,9 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
     return 0;
 }
 
-template <bool A_MN, bool B_MN, bool OUT_F32>
+template <bool A_MN, bool B_MN, bool OUT_F32, int EPI = EPI_GENERIC>
 static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-    auto kern = gemm_tcgen05_2cta_kernel<A_MN, B_MN, OUT_F32>;
+    auto kern = gemm_tcgen05_2cta_kernel<A_MN, B_MN, OUT_F32, EPI>;
     static int configured[kMaxDevices] = {0};
     VB_CHECK_CUDA(ensure_dyn_smem(kern, Cfg2::SMEM_BYTES, configured));
     const int tiles = ((p.M + 255) / 256) * ((p.N + 255) / 256) * p.splits;
@@ -845,8 +858,29 @@ int gemm(const vb_gemm_args& a, cudaStream_t st) {
         else               rc = make_tmap_bf16(&tb, a.B, a.N, a.K, a.ldb, BLOCK_K);
         if (rc) return rc;
         if (!a.d_fp32) {
-            if (!a.a_mn_major && !a.b_mn_major) return launch2<false, false, false>(ta, tb, p, st);
-            if (!a.a_mn_major && a.b_mn_major) return launch2<false, true, false>(ta, tb, p, st);
+            // specialised epilogues for the shapes of the layer (forward and input-gradient GEMMs); anything else: generic
+            const bool drop = a.dropout_p > 0.0f, add = a.addend != nullptr;
+            int epi = EPI_GENERIC;
+            if (a.epilogue == VB_EPI_GELU && !drop && !add) epi = EPI_GELU_FWD;
+            else if (a.epilogue == VB_EPI_DGELU && !drop && !add) epi = EPI_DGELU_BWD;
+            else if (a.epilogue == VB_EPI_NONE) epi = add ? (drop ? EPI_DROP_RESID : EPI_RESID) : (drop ? EPI_GENERIC : EPI_BIAS);
+            if (!a.a_mn_major && !a.b_mn_major) {
+                switch (epi) {
+                    case EPI_BIAS: return launch2<false, false, false, EPI_BIAS>(ta, tb, p, st);
+                    case EPI_RESID: return launch2<false, false, false, EPI_RESID>(ta, tb, p, st);
+                    case EPI_DROP_RESID: return launch2<false, false, false, EPI_DROP_RESID>(ta, tb, p, st);
+                    case EPI_GELU_FWD: return launch2<false, false, false, EPI_GELU_FWD>(ta, tb, p, st);
+                    default: return launch2<false, false, false>(ta, tb, p, st);
+                }
+            }
+            if (!a.a_mn_major && a.b_mn_major) {
+                switch (epi) {
+                    case EPI_BIAS: return launch2<false, true, false, EPI_BIAS>(ta, tb, p, st);
+                    case EPI_RESID: return launch2<false, true, false, EPI_RESID>(ta, tb, p, st);
+                    case EPI_DGELU_BWD: return launch2<false, true, false, EPI_DGELU_BWD>(ta, tb, p, st);
+                    default: return launch2<false, true, false>(ta, tb, p, st);
+                }
+            }
             if (a.a_mn_major && a.b_mn_major) return launch2<true, true, false>(ta, tb, p, st);
             return launch2<true, false, false>(ta, tb, p, st);
         } else {
