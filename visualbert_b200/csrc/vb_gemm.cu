@@ -620,11 +620,13 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             uint32_t v[2][16];
             tmem_ld_32x32b_x16(taddr0, v[0]);
             // chunks in groups of kExAhead: inside a group every buffer index is static; the group loop is NOT unrolled (code size)
-            static_assert(NCH % kExAhead == 0, "chunk groups");
+            // (epilogues without a prefetched operand only need the 2-deep TMEM double buffer: groups of 2 halve their code again)
+            constexpr int kGroup = (EPI == EPI_GELU_FWD || EPI == EPI_BIAS) ? 2 : kExAhead;
+            static_assert(NCH % kGroup == 0, "chunk groups");
 #pragma unroll 1
-            for (int k0 = 0; k0 < NCH; k0 += kExAhead) {
+            for (int k0 = 0; k0 < NCH; k0 += kGroup) {
 #pragma unroll
-                for (int kk = 0; kk < kExAhead; ++kk) {
+                for (int kk = 0; kk < kGroup; ++kk) {
                     const int k = k0 + kk;
                     tmem_ld_wait();
                     if (k + 1 < NCH) tmem_ld_32x32b_x16(taddr0 + (k + 1) * 16, v[(kk + 1) & 1]);
