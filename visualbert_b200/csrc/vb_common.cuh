@@ -60,6 +60,26 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+// same, for a kernel launched as clusters of `cluster` CTAs along x (cluster size chosen at launch, not at compile time)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster,
+                                      Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 #endif
 
 struct ProfScope {
@@ -364,11 +384,23 @@ __device__ __forceinline__ void umma_bf16_2cta(uint32_t d_tmem, uint64_t a_desc,
         "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// commit: arrive on the mbarrier at this offset in BOTH CTAs of the pair when the MMAs issued so far retire
-__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
+// commit: when the MMAs issued so far retire, arrive on the mbarrier at this offset in every CTA of `cta_mask`
+// (bit i = CTA rank i of the cluster; 3 = both CTAs of the first pair)
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar, uint32_t cta_mask = 3u) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-                 "h"(static_cast<uint16_t>(3))
+                 "h"(static_cast<uint16_t>(cta_mask))
                  : "memory");
+}
+// TMA load multicast to the CTAs of `cta_mask`: the box lands at the same CTA-relative offset in each of them and the
+// bytes are credited to the barrier at this offset in the LEADER of each destination CTA's pair (peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_2cta_mc(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c_inner, int c_outer,
+                                                    uint32_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & 0xFEFFFFFFu), "r"(c_inner), "r"(c_outer),
+          "h"(static_cast<uint16_t>(cta_mask))
+        : "memory");
 }
 
 // 32 lanes x 32 columns of 32-bit: thread i of the warp receives row (lane base + i), 32 columns.

@@ -451,8 +451,13 @@ __host__ __device__ constexpr uint32_t make_idesc_m(int m, int n, bool a_mn, boo
            (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-template <bool A_MN, bool B_MN, bool OUT_F32, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+// CL = 4 ("quad"): two CTA pairs per cluster work on the SAME 256 columns of B and on neighbouring 256-row blocks of A.
+// Each CTA fetches only half of its 128 x 64 part of the B tile and TMA-multicasts it to the CTA holding the same part
+// in the other pair, so the L2 -> SM operand traffic per pair and k-block drops from 64 KB to 48 KB. (These GEMMs run at
+// the L2 bandwidth limit — see DESIGN.md — which is why this matters.) A stage may only be refilled once BOTH pairs have
+// consumed it (the other pair writes into it too): empty[s] counts one commit from each pair.
+template <bool A_MN, bool B_MN, bool OUT_F32, int EPI, int CL = 2>
+__global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmParams p) {
     using C = Cfg2;
@@ -462,7 +467,13 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
+    constexpr bool kQuad = CL == 4;
+    static_assert(CL == 2 || CL == 4, "cluster of one or two CTA pairs");
+    static_assert(!kQuad || !OUT_F32, "the quad variant has no split-K path");
+    const uint32_t crank = cluster_ctarank();
+    const uint32_t rank = crank & 1u;          // rank inside the CTA pair
+    const uint32_t pair = crank >> 1;          // 0, or 0/1 in a quad
+    const uint32_t leader_rank = crank & ~1u;  // cluster rank of this pair's leader
     const bool leader = rank == 0;
 
     auto a_tile = [&](int s) { return base + s * C::STAGE_BYTES; };
@@ -480,7 +491,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages2; ++s) {
             mbar_init(full_bar(s), 2);
-            mbar_init(empty_bar(s), 1);
+            mbar_init(empty_bar(s), kQuad ? 2 : 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar(s), 1);
@@ -500,23 +511,35 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int m_blocks = (p.M + 255) / 256;
     const int n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
     const int k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
-    const int num_tiles = m_blocks * n_blocks * p.splits;
-    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    // quad: a "tile" of the loops below is a pair of m-blocks (2j, 2j + 1) x one n-block; pair 1 of an odd tail works on
+    // an all-out-of-bounds block (TMA zero fill, epilogue rows masked) so the four CTAs stay in step
+    const int num_tiles = kQuad ? ((m_blocks + 1) / 2) * n_blocks : m_blocks * n_blocks * p.splits;
+    const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
+    auto tile_of = [&](int t) {
+        TileCoord c = decode_tile(t, n_blocks, kQuad ? 1 : p.splits, k_blocks);
+        if constexpr (kQuad) c.m_blk = c.m_blk * 2 + static_cast<int>(pair);
+        return c;
+    };
+    const uint32_t empty_mask = kQuad ? 0xFu : 3u, pair_mask = 3u << (2 * pair);
 
+    // Epilogues that read a second operand (residual / gelu') hold the whole tile row of it in registers (see below): the
+    // four control warps hand registers to the eight epilogue warps (128 * 72 + 256 * 216 = 384 * 168).
+    constexpr bool kDeepEx = !OUT_F32 && (EPI == EPI_RESID || EPI == EPI_DROP_RESID || EPI == EPI_DGELU_BWD);
     if (warp == 0) {
+        if constexpr (kDeepEx) reg_dec<72>();
         {
             // ---------------- TMA producer (both CTAs; converged warp, one elected lane issues) ----------------
             int stage = 0;
             uint32_t phase = 0;
             for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-                const TileCoord tc = decode_tile(t, n_blocks, p.splits, k_blocks);
+                const TileCoord tc = tile_of(t);
                 const int m0 = tc.m_blk * 256 + static_cast<int>(rank) * 128;
                 const int n0 = tc.n_blk * BLOCK_N + static_cast<int>(rank) * 128;
                 for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     if (elect_one()) {
                     if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
-                    else mbar_arrive_remote(full_bar(stage), 0);
+                    else mbar_arrive_remote(full_bar(stage), leader_rank);
                     if constexpr (!A_MN) {
                         tma_load_2d_2cta(a_tile(stage), &tmA, full_bar(stage), kb * BLOCK_K, m0);
                     } else {
@@ -524,7 +547,14 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                         for (int i = 0; i < 2; ++i)
                             tma_load_2d_2cta(a_tile(stage) + i * kAtomBytes, &tmA, full_bar(stage), m0 + i * 64, kb * BLOCK_K);
                     }
-                    if constexpr (!B_MN) {
+                    if constexpr (kQuad) {
+                        // this CTA's half (64 of the 128 B columns it holds: one 8 KB swizzle-atom block in either major),
+                        // multicast to the CTA with the same pair rank in the other pair
+                        const uint32_t mc = rank ? 0xAu : 0x5u;
+                        const uint32_t dst = b_tile(stage) + pair * kAtomBytes;
+                        if constexpr (!B_MN) tma_load_2d_2cta_mc(dst, &tmB, full_bar(stage), kb * BLOCK_K, n0 + static_cast<int>(pair) * 64, mc);
+                        else                 tma_load_2d_2cta_mc(dst, &tmB, full_bar(stage), n0 + static_cast<int>(pair) * 64, kb * BLOCK_K, mc);
+                    } else if constexpr (!B_MN) {
                         tma_load_2d_2cta(b_tile(stage), &tmB, full_bar(stage), kb * BLOCK_K, n0);
                     } else {
 #pragma unroll
@@ -538,6 +568,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
         }
     } else if (warp == 1) {
+        if constexpr (kDeepEx) reg_dec<72>();
         if (leader) {
             // ---------------- MMA issuer (leader CTA only): converged warp, one elected lane issues ----------------
             constexpr uint32_t idesc = make_idesc_m(256, BLOCK_N, A_MN, B_MN);
@@ -549,7 +580,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             uint32_t phase = 0;
             int it = 0;
             for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
-                const TileCoord tc = decode_tile(t, n_blocks, p.splits, k_blocks);
+                const TileCoord tc = tile_of(t);
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -563,8 +594,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
                             umma_bf16_2cta(d_tmem, ad.at(k * a_kstep), bd.at(k * b_kstep), idesc, (kb > tc.kb_begin || k > 0) ? 1u : 0u);
-                        umma_commit_2cta(empty_bar(stage));
-                        if (kb == tc.kb_end - 1) umma_commit_2cta(tfull_bar(acc));
+                        umma_commit_2cta(empty_bar(stage), empty_mask);
+                        if (kb == tc.kb_end - 1) umma_commit_2cta(tfull_bar(acc), pair_mask);
                     }
                     __syncwarp();
                     if (++stage == kStages2) { stage = 0; phase ^= 1u; }
@@ -575,6 +606,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             for (int j = (it >= 2 ? it - 2 : 0); j < it; ++j) mbar_wait(tempty_bar(j & 1), (j >> 1) & 1);
         }
     } else if (warp >= 4) {
+        if constexpr (kDeepEx) reg_inc<216>();
         // ---------------- epilogue (both CTAs, 128 rows each) ----------------
         const int ew = warp - 4;
         const int q = warp & 3;
@@ -584,7 +616,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         constexpr int NCH = BLOCK_N / 2 / 16;
         int it = 0;
         for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
-            const TileCoord tc = decode_tile(t, n_blocks, p.splits, k_blocks);
+            const TileCoord tc = tile_of(t);
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const bool has_bias = p.bias != nullptr;
@@ -599,11 +631,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
             const int row = tc.m_blk * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;
             const int col0 = tc.n_blk * BLOCK_N + half * (BLOCK_N / 2);
-            // Residual / gelu' operand of this thread's row: one 32-byte load per 16-column chunk. The loads are
-            // row-strided DRAM accesses (~1 us each under load), so kExAhead of them are kept in flight and the
-            // first batch is issued BEFORE waiting for the accumulator.
             constexpr int kExAhead = 4;
-            uint32_t ex[kExAhead][8];
             const bf16* exp_ = nullptr;
             if constexpr (!OUT_F32) {
                 constexpr bool kWantAdd = EPI == EPI_RESID || EPI == EPI_DROP_RESID;
@@ -611,41 +639,83 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 else if (EPI == EPI_DGELU_BWD || (EPI == EPI_GENERIC && p.epilogue == VB_EPI_DGELU)) exp_ = p.aux_in + static_cast<long long>(row) * p.ld_aux;
                 if (row >= p.M) exp_ = nullptr;
             }
-#pragma unroll
-            for (int k = 0; k < kExAhead; ++k)
-                if (exp_ != nullptr && col0 + k * 16 < p.N) ldg_v8(exp_ + col0 + k * 16, ex[k]);
-            mbar_wait(tfull_bar(acc), acc_phase);
-            tcgen05_fence_after();
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + half * (BLOCK_N / 2);
             uint32_t v[2][16];
-            tmem_ld_32x32b_x16(taddr0, v[0]);
-            // chunks in groups of kExAhead: inside a group every buffer index is static; the group loop is NOT unrolled (code size)
-            // (epilogues without a prefetched operand only need the 2-deep TMEM double buffer: groups of 2 halve their code again)
-            constexpr int kGroup = (EPI == EPI_GELU_FWD || EPI == EPI_BIAS) ? 2 : kExAhead;
-            static_assert(NCH % kGroup == 0, "chunk groups");
+            if constexpr (kDeepEx) {
+                // The whole tile row of the operand (8 chunks = 256 bytes per thread) is requested BEFORE waiting for the
+                // accumulator, i.e. while this tile's main loop is still running: nothing of the DRAM latency is left in the
+                // epilogue. Two banks of four buffers; the group loop stays rolled (code size) and picks its bank with
+                // selects.
+                static_assert(NCH == 2 * kExAhead, "two banks");
+                uint32_t exA[kExAhead][8], exB[kExAhead][8];
+#pragma unroll
+                for (int k = 0; k < kExAhead; ++k)
+                    if (exp_ != nullptr && col0 + k * 16 < p.N) ldg_v8(exp_ + col0 + k * 16, exA[k]);
+#pragma unroll
+                for (int k = 0; k < kExAhead; ++k)
+                    if (exp_ != nullptr && col0 + (k + kExAhead) * 16 < p.N) ldg_v8(exp_ + col0 + (k + kExAhead) * 16, exB[k]);
+                mbar_wait(tfull_bar(acc), acc_phase);
+                tcgen05_fence_after();
+                tmem_ld_32x32b_x16(taddr0, v[0]);
 #pragma unroll 1
-            for (int k0 = 0; k0 < NCH; k0 += kGroup) {
+                for (int k0 = 0; k0 < NCH; k0 += kExAhead) {
 #pragma unroll
-                for (int kk = 0; kk < kGroup; ++kk) {
-                    const int k = k0 + kk;
-                    tmem_ld_wait();
-                    if (k + 1 < NCH) tmem_ld_32x32b_x16(taddr0 + (k + 1) * 16, v[(kk + 1) & 1]);
-                    const int col = col0 + k * 16;
-                    if (row < p.M && col < p.N) {
-                        float x[16];
+                    for (int kk = 0; kk < kExAhead; ++kk) {
+                        const int k = k0 + kk;
+                        tmem_ld_wait();
+                        if (k + 1 < NCH) tmem_ld_32x32b_x16(taddr0 + (k + 1) * 16, v[(kk + 1) & 1]);
+                        const int col = col0 + k * 16;
+                        if (row < p.M && col < p.N) {
+                            float x[16];
+                            uint32_t e[8];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[kk & 1][i]);
-                        epilogue16<OUT_F32, EPI>(p, row, col, has_bias ? sb + half * (BLOCK_N / 2) + k * 16 : nullptr, ex[kk], x);
+                            for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[kk & 1][i]);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) e[i] = k0 ? exB[kk][i] : exA[kk][i];
+                            epilogue16<OUT_F32, EPI>(p, row, col, has_bias ? sb + half * (BLOCK_N / 2) + k * 16 : nullptr, e, x);
+                        }
                     }
-                    // buffer kk is free again: refill it with the operand of chunk k + kExAhead
-                    if (k + kExAhead < NCH && exp_ != nullptr && col0 + (k + kExAhead) * 16 < p.N)
-                        ldg_v8(exp_ + col0 + (k + kExAhead) * 16, ex[kk]);
+                }
+            } else {
+                // Residual / gelu' operand of this thread's row (generic kernel): one 32-byte load per 16-column chunk,
+                // kExAhead of them in flight, the first batch issued BEFORE waiting for the accumulator.
+                uint32_t ex[kExAhead][8];
+#pragma unroll
+                for (int k = 0; k < kExAhead; ++k)
+                    if (exp_ != nullptr && col0 + k * 16 < p.N) ldg_v8(exp_ + col0 + k * 16, ex[k]);
+                mbar_wait(tfull_bar(acc), acc_phase);
+                tcgen05_fence_after();
+                tmem_ld_32x32b_x16(taddr0, v[0]);
+                // chunks in groups: inside a group every buffer index is static; the group loop is NOT unrolled (code size)
+                // (epilogues without a prefetched operand only need the 2-deep TMEM double buffer: groups of 2 halve their code again)
+                constexpr int kGroup = (EPI == EPI_GELU_FWD || EPI == EPI_BIAS) ? 2 : kExAhead;
+                static_assert(NCH % kGroup == 0, "chunk groups");
+#pragma unroll 1
+                for (int k0 = 0; k0 < NCH; k0 += kGroup) {
+#pragma unroll
+                    for (int kk = 0; kk < kGroup; ++kk) {
+                        const int k = k0 + kk;
+                        tmem_ld_wait();
+                        if (k + 1 < NCH) tmem_ld_32x32b_x16(taddr0 + (k + 1) * 16, v[(kk + 1) & 1]);
+                        const int col = col0 + k * 16;
+                        if (row < p.M && col < p.N) {
+                            float x[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[kk & 1][i]);
+                            epilogue16<OUT_F32, EPI>(p, row, col, has_bias ? sb + half * (BLOCK_N / 2) + k * 16 : nullptr, ex[kk], x);
+                        }
+                        // buffer kk is free again: refill it with the operand of chunk k + kExAhead
+                        if (k + kExAhead < NCH && exp_ != nullptr && col0 + (k + kExAhead) * 16 < p.N)
+                            ldg_v8(exp_ + col0 + (k + kExAhead) * 16, ex[kk]);
+                    }
                 }
             }
             tcgen05_fence_before();
             if (leader) mbar_arrive(tempty_bar(acc));
-            else mbar_arrive_remote(tempty_bar(acc), 0);
+            else mbar_arrive_remote(tempty_bar(acc), leader_rank);
         }
+    } else {
+        if constexpr (kDeepEx) reg_dec<72>();   // warps 2 and 3 release their share as well (the pool is per CTA)
     }
 
     tcgen05_fence_before();
@@ -784,10 +854,54 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
     if (clusters > tiles) clusters = tiles;
     {
         ProfScope ps(st, OUT_F32 ? PROF_GEMM_WGRAD : (B_MN ? PROF_GEMM_DGRAD : PROF_GEMM_FWD), 2.0 * p.M * p.N * p.K, 1);
-        VB_CHECK_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(kThreads), Cfg2::SMEM_BYTES, st, ta, tb, p));
+        VB_CHECK_CUDA(launch_pdl_cluster(kern, dim3(2 * clusters), dim3(kThreads), Cfg2::SMEM_BYTES, st, 2, ta, tb, p));
     }
     VB_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+// Quad variant (two CTA pairs per cluster sharing the B tile by TMA multicast). Returns -1 when clusters of four cannot be
+// placed on this device (the caller then uses the pair kernel).
+template <bool B_MN, int EPI>
+static int launch4(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+    auto kern = gemm_tcgen05_2cta_kernel<false, B_MN, false, EPI, 4>;
+    static int configured[kMaxDevices] = {0};
+    static int resident[kMaxDevices] = {0};  // clusters of four that fit on the device at once (0 = not asked yet)
+    VB_CHECK_CUDA(ensure_dyn_smem(kern, Cfg2::SMEM_BYTES, configured));
+    const int dev = current_device();
+    if (resident[dev] == 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(4 * (num_sms() / 4));
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = Cfg2::SMEM_BYTES;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+        resident[dev] = n > 0 ? n : -1;
+        if (getenv("VB_GEMM_DEBUG")) fprintf(stderr, "[vb_gemm] device %d: %d clusters of four CTAs fit (%d SMs)\n", dev, n, num_sms());
+    }
+    if (resident[dev] < 0) return -1;
+    const int tiles = (((p.M + 255) / 256 + 1) / 2) * ((p.N + 255) / 256);
+    int clusters = resident[dev] < num_sms() / 4 ? resident[dev] : num_sms() / 4;
+    if (clusters > tiles) clusters = tiles;
+    {
+        ProfScope ps(st, B_MN ? PROF_GEMM_DGRAD : PROF_GEMM_FWD, 2.0 * p.M * p.N * p.K, 1);
+        VB_CHECK_CUDA(launch_pdl_cluster(kern, dim3(4 * clusters), dim3(kThreads), Cfg2::SMEM_BYTES, st, 4, ta, tb, p));
+    }
+    VB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+// VB_GEMM_QUAD=1 opts in to the quad kernels. Off by default: measured on B200 (r02, scripts/gpu_check_gemm.py perf) only
+// 33 clusters of four are co-resident (132 of 148 SMs) and the saved L2 traffic does not make up for the idle SMs — the
+// layer's GEMMs are 5-9 % slower than on the pair kernel (DESIGN.md "negative results").
+static bool use_quad() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VB_GEMM_QUAD"); v = (e != nullptr && atoi(e) == 1) ? 1 : 0; }
+    return v == 1;
 }
 
 bool pdl_enabled() {
@@ -866,6 +980,30 @@ int gemm(const vb_gemm_args& a, cudaStream_t st) {
             if (a.epilogue == VB_EPI_GELU && !drop && !add) epi = EPI_GELU_FWD;
             else if (a.epilogue == VB_EPI_DGELU && !drop && !add) epi = EPI_DGELU_BWD;
             else if (a.epilogue == VB_EPI_NONE) epi = add ? (drop ? EPI_DROP_RESID : EPI_RESID) : (drop ? EPI_GENERIC : EPI_BIAS);
+            // quad clusters for the tall activation GEMMs of the layer (at least two 256-row blocks to pair up)
+            if (use_quad() && epi != EPI_GENERIC && !a.a_mn_major && a.M > 256) {
+                CUtensorMap tq;  // K-major B is fetched in 64-row boxes (half of a CTA's part), MN-major B already is
+                int q = 1;
+                if (!a.b_mn_major) {
+                    rc = make_tmap_bf16(&tq, a.B, a.K, a.N, a.ldb, 64);
+                    if (rc) return rc;
+                    switch (epi) {
+                        case EPI_BIAS: q = launch4<false, EPI_BIAS>(ta, tq, p, st); break;
+                        case EPI_RESID: q = launch4<false, EPI_RESID>(ta, tq, p, st); break;
+                        case EPI_DROP_RESID: q = launch4<false, EPI_DROP_RESID>(ta, tq, p, st); break;
+                        case EPI_GELU_FWD: q = launch4<false, EPI_GELU_FWD>(ta, tq, p, st); break;
+                        default: q = -1; break;
+                    }
+                } else {
+                    switch (epi) {
+                        case EPI_BIAS: q = launch4<true, EPI_BIAS>(ta, tb, p, st); break;
+                        case EPI_RESID: q = launch4<true, EPI_RESID>(ta, tb, p, st); break;
+                        case EPI_DGELU_BWD: q = launch4<true, EPI_DGELU_BWD>(ta, tb, p, st); break;
+                        default: q = -1; break;
+                    }
+                }
+                if (q >= 0) return q;  // launched (0) or failed (> 0); -1: no room for clusters of four, fall through
+            }
             if (!a.a_mn_major && !a.b_mn_major) {
                 switch (epi) {
                     case EPI_BIAS: return launch2<false, false, false, EPI_BIAS>(ta, tb, p, st);
