@@ -11,10 +11,15 @@
 //                              the consumed scores by the softmax threads: no shared-memory round trip), B = V (MN-major)
 //   warp 2       TMEM allocator (512 columns: S0 | S1 | O0 | O1)
 //   warp 3       stages the item's additive key-mask row (x log2 e) in shared memory
-//   warps 4-7    softmax warp-group 0, warps 8-11 softmax warp-group 1: tile n of the CTA's tile sequence belongs to
-//                group n % 2 and to TMEM buffers n % 2, so the QK^T of tile n+2 and the P V of tile n+1 run under the
-//                softmax of the other group. One thread per query row (row == TMEM lane): two passes over the row
-//                straight out of TMEM (max, then exp2 / sum / dropout / bf16 -> TMEM), no cross-thread exchange.
+//   warps 4-19   softmax: tile n of the CTA's tile sequence belongs to group n % 2 and to TMEM buffers n % 2, so the
+//                QK^T of tile n+2 and the P V of tile n+1 run under the softmax of the other group. A group is TWO
+//                warp-groups (a: warps 4-7 / 8-11, b: warps 12-15 / 16-19): a query row (== TMEM lane) is shared by one
+//                thread of each, a taking the first half of the key chunks and b the second (a warp may only touch its
+//                own lane quarter of TMEM, so more threads per row means more warps per quarter). Two passes over the
+//                row straight out of TMEM (max, then exp2 / sum / dropout / bf16 -> TMEM); the two halves exchange the
+//                row maximum and the row sum through shared memory (two 256-thread named barriers per tile). With seq =
+//                128 + r every other tile is the short one, i.e. one group is mostly idle lanes: the time of a tile is
+//                the latency of ONE row, which the column split halves.
 //
 // Lane balance for seq = 128 + r (the benchmark's 164 = 128 + 36): the short second tile would keep only lane
 // quarter 0 (and a sliver of quarter 1) busy, i.e. always the same SM sub-partition. Its rows are therefore placed at a
@@ -29,7 +34,8 @@ namespace {
 
 constexpr int kQRows = 128;           // query rows per tile (UMMA M)
 constexpr int kWgThreads = 128;       // one softmax warp-group
-constexpr int kThreadsTc = 128 + 2 * kWgThreads;
+constexpr int kSoftmaxThreads = 4 * kWgThreads;   // 2 groups x 2 column halves
+constexpr int kThreadsTc = 128 + kSoftmaxThreads;
 constexpr int kMaxNpad = 192;         // two S buffers of <= 192 columns + two O buffers of 64 = 512 TMEM columns
 constexpr int kStagesTc = 2;
 
@@ -63,6 +69,7 @@ struct TcLayout {  // shared-memory carve-up (bytes from the 1 KB-aligned base)
     int q2_off;       // the two windows sit BETWEEN the two stages: >= 16 KB of valid shared memory on both sides
     int stage1_off;
     int bias_off;     // fp32 [2][kMaxNpad]
+    int xchg_off;     // fp32 [2 groups][max | sum][2 halves][128 rows]
     int bar_off;
     int tmem_ptr_off;
     int total;
@@ -75,7 +82,8 @@ __host__ __device__ inline TcLayout tc_layout(int npad, int r2pad) {
     L.q2_off = L.stage_bytes;
     L.stage1_off = L.q2_off + 2 * L.q2_bytes;
     L.bias_off = L.stage1_off + L.stage_bytes;
-    L.bar_off = L.bias_off + 2 * kMaxNpad * 4;
+    L.xchg_off = L.bias_off + 2 * kMaxNpad * 4;
+    L.bar_off = L.xchg_off + 2 * 2 * 2 * kQRows * 4;
     L.tmem_ptr_off = L.bar_off + 16 * 8;
     L.total = L.tmem_ptr_off + 16 + 1024;
     return L;
@@ -97,6 +105,11 @@ __device__ __forceinline__ int tile2_offset(int li, int r2pad) {
     const int o = (li & 3) * 32;
     return o < lim ? o : lim;
 }
+
+// Which of the item's tiles is the n-th tile of the CTA's sequence. (Measured, r02: letting odd items run their short tile
+// first — so that both softmax groups alternate full and short tiles — is SLOWER, 105 vs 95 us: the MMA warp issues the
+// P V products in tile order, so the groups end up waiting for each other.)
+__device__ __forceinline__ int tile_in_item(int n, int li, int nq) { return n - li * nq; }
 
 __global__ void __launch_bounds__(kThreadsTc, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQ2,
@@ -130,9 +143,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             mbar_init(bar(FULL0 + s), 2);             // TMA producer (expect_tx) + the mask-row stager
             mbar_init(bar(EMPTY0 + s), 1);            // tcgen05.commit after the item's last MMA
             mbar_init(bar(SFULL0 + s), 1);
-            mbar_init(bar(PFULL0 + s), kWgThreads);
+            mbar_init(bar(PFULL0 + s), 2 * kWgThreads);
             mbar_init(bar(OFULL0 + s), 1);
-            mbar_init(bar(OEMPTY0 + s), kWgThreads);
+            mbar_init(bar(OEMPTY0 + s), 2 * kWgThreads);
         }
         fence_barrier_init();
     }
@@ -150,7 +163,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int n_local = (total - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
     const int n_tiles = n_local * nq;
 
+    // 640 threads x 96 registers at launch: the four control warps keep 40, the sixteen softmax warps take 104
     if (warp == 0) {
+        reg_dec<40>();
         if (lane == 0) {
             // ---------------- TMA producer ----------------
             const uint32_t stage_tx = static_cast<uint32_t>(kQRows * 128 + 2 * npad * 128 + (nq == 2 ? tp.r2pad * 128 : 0));
@@ -167,12 +182,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             }
         }
     } else if (warp == 1) {
+        reg_dec<40>();
         {
             // ---------------- MMA issuer: the whole warp runs the loop converged, one elected lane issues ----------------
             const uint32_t idesc_qk = idesc_bf16(kQRows, npad, false, false);
             const uint32_t idesc_pv = idesc_bf16(kQRows, kHd, false, true);
             auto issue_s = [&](int n) {
-                const int li = n / nq, t = n - li * nq;
+                const int li = n / nq, t = tile_in_item(n, li, nq);
                 const int s = li % kStagesTc, bf = n & 1;
                 mbar_wait(bar(FULL0 + s), (li / kStagesTc) & 1);
                 tcgen05_fence_after();
@@ -188,7 +204,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 if (tp.dbg != nullptr && blockIdx.x == 0 && n < 32 && lane == 0) tp.dbg[n * 16 + 12] = clock64();
             };
             auto issue_pv = [&](int n) {
-                const int li = n / nq, t = n - li * nq;
+                const int li = n / nq, t = tile_in_item(n, li, nq);
                 const int s = li % kStagesTc, bf = n & 1;
                 const uint32_t ph = (n >> 1) & 1;
                 const bool stamp = tp.dbg != nullptr && blockIdx.x == 0 && n < 32 && lane == 0;
@@ -198,13 +214,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 mbar_wait(bar(OEMPTY0 + bf), ph ^ 1u);
                 tcgen05_fence_after();
                 if (stamp) tp.dbg[n * 16 + 10] = clock64();
-                const int ksteps = npad / 16;
+                const int ksteps = npad / 16, ca = (ksteps + 1) / 2;
                 const UmmaDesc dv = make_umma_desc_sw128(v_tile(s), 0, 1024);
                 if (elect_one()) {
-                    // A = P: bf16 in TMEM, 16 keys = 8 columns; B = V: MN-major [keys x 128 B], 16 key rows per step
-                    for (int k = 0; k < ksteps; ++k) umma_bf16_ts(tmem_o(bf), tmem_s(bf) + k * 8, dv.at(k * 2048), idesc_pv, k > 0 ? 1u : 0u);
+                    // A = P: bf16 in TMEM, 16 keys = 8 columns; B = V: MN-major [keys x 128 B], 16 key rows per step.
+                    // The first ca chunks of P sit at the start of the score buffer, the rest at the start of the second
+                    // half's own score columns (each half overwrites only what it has consumed itself).
+                    for (int k = 0; k < ksteps; ++k) {
+                        const uint32_t pa = tmem_s(bf) + static_cast<uint32_t>(k < ca ? k * 8 : 16 * ca + (k - ca) * 8);
+                        umma_bf16_ts(tmem_o(bf), pa, dv.at(k * 2048), idesc_pv, k > 0 ? 1u : 0u);
+                    }
                     umma_commit(bar(OFULL0 + bf));
-                    if (t == nq - 1) umma_commit(bar(EMPTY0 + s));  // every MMA of the item has retired: Q / K / V are free
+                    if (n - li * nq == nq - 1) umma_commit(bar(EMPTY0 + s));  // every MMA of the item has retired: Q / K / V are free
                 }
                 __syncwarp();
                 if (stamp) tp.dbg[n * 16 + 11] = clock64();
@@ -217,7 +238,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 if (n + 2 < n_tiles) issue_s(n + 2);
             }
         }
+    } else if (warp == 2) {
+        reg_dec<40>();
     } else if (warp == 3) {
+        reg_dec<40>();
         // ---------------- additive key-mask row of the item, log2 domain; -inf on the padding keys ----------------
         for (int li = 0; li < n_local; ++li) {
             const int item = blockIdx.x + li * gridDim.x;
@@ -231,17 +255,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             if (lane == 0) mbar_arrive(bar(FULL0 + s));
         }
     } else if (warp >= 4) {
-        // ---------------- softmax + epilogue: one thread per query row ----------------
-        const int g = (warp - 4) >> 2;           // warp-group = TMEM buffer
+        reg_inc<104>();
+        // ---------------- softmax + epilogue: two threads per query row (column halves a / b) ----------------
+        const int g = ((warp - 4) >> 2) & 1;     // group = TMEM buffer
+        const int hb = (warp - 4) >> 3;          // 0: first half of the key chunks (a), 1: second half (b)
         const int q4 = warp & 3;                 // TMEM lane quarter of this warp
         const int r = q4 * 32 + lane;            // row inside the tile == TMEM lane
         const uint32_t lane_sel = static_cast<uint32_t>(q4 * 32) << 16;
         const float sc2 = p.scale * kLog2e;
         const int nchunk = npad / 16;
+        const int ca = (nchunk + 1) / 2;                       // chunks [0, ca) -> a, [ca, nchunk) -> b
+        const int c_lo = hb ? ca : 0, c_hi = hb ? nchunk : ca;
+        const uint32_t p_col0 = hb ? static_cast<uint32_t>(16 * ca) : 0u;   // where this half's bf16 P starts
+        float* xch = reinterpret_cast<float*>(smem + L.xchg_off) + g * (4 * kQRows);  // [max | sum][half][row]
         const bool drop = p.drop_scale != 0.f;
         const int np64 = tp.nkb * kBlk;
         for (int n = g; n < n_tiles; n += 2) {
-            const int li = n / nq, t = n - li * nq;
+            const int li = n / nq, t = tile_in_item(n, li, nq);
             const int item = blockIdx.x + li * gridDim.x;
             const int b = item / p.A, h = item % p.A;
             const int s = li % kStagesTc;
@@ -266,15 +296,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 if (tp.nkb > 2) kw2 = kp[2];
             }
             const float* sbias = sbias_all + s * kMaxNpad;
-            const bool stamp = tp.dbg != nullptr && blockIdx.x == 0 && (threadIdx.x & 127) == 0 && n < 32;
+            const bool stamp = tp.dbg != nullptr && blockIdx.x == 0 && hb == 0 && (threadIdx.x & 127) == 0 && n < 32;
             if (stamp) tp.dbg[n * 16 + 0] = clock64();
             mbar_wait(bar(FULL0 + s), (li / kStagesTc) & 1);   // mask row staged (and visible) for this item
             mbar_wait(bar(SFULL0 + g), ph);
             tcgen05_fence_after();
             if (stamp) tp.dbg[n * 16 + 1] = clock64();
             const uint32_t ts = tmem_s(g) + lane_sel;
-            float m = 0.f, lsum = 1.f;
-            if (wvalid) {
+            float m = -INFINITY, lsum = 0.f;
+            if (wvalid && c_lo < c_hi) {
                 // ---- pass 1: row maximum of the scaled, masked scores (next chunk's tcgen05.ld in flight) ----
                 float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
                 auto pass1 = [&](const uint32_t (&v)[16], int c) {
@@ -289,21 +319,24 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     }
                 };
                 {
-                    uint32_t va[16], vb_[16];
-                    tmem_ld_32x32b_x16(ts, va);
-                    for (int c = 0; c < nchunk; c += 2) {
+                    // one buffer: with four softmax warps per scheduler the other warps cover the tcgen05.ld latency, and the
+                    // registers a second buffer would take are what keeps this loop free of spills at 104 per thread
+                    // (32-column loads for the maximum were measured slower: 104 vs 96 us)
+                    uint32_t va[16];
+                    for (int c = c_lo; c < c_hi; ++c) {
+                        tmem_ld_32x32b_x16(ts + c * 16, va);
                         tmem_ld_wait();
-                        if (c + 1 < nchunk) tmem_ld_32x32b_x16(ts + (c + 1) * 16, vb_);
                         pass1(va, c);
-                        if (c + 1 < nchunk) {
-                            tmem_ld_wait();
-                            if (c + 2 < nchunk) tmem_ld_32x32b_x16(ts + (c + 2) * 16, va);
-                            pass1(vb_, c + 1);
-                        }
                     }
                 }
                 m = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-                if (stamp) tp.dbg[n * 16 + 2] = clock64();
+            }
+            // row maximum over both halves
+            xch[hb * kQRows + r] = m;
+            named_bar_sync(1 + g, 2 * kWgThreads);
+            m = fmaxf(m, xch[(hb ^ 1) * kQRows + r]);
+            if (stamp) tp.dbg[n * 16 + 2] = clock64();
+            if (wvalid && c_lo < c_hi) {
                 // ---- pass 2: probabilities, row sum, dropout, bf16 P written over the consumed scores in TMEM ----
                 float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
                 auto pass2 = [&](const uint32_t (&v)[16], int c) {
@@ -329,20 +362,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     uint32_t w8[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) w8[i] = pack_bf16x2(pr[2 * i], pr[2 * i + 1]);
-                    tmem_st_32x32b_x8(ts + c * 8, w8);   // columns 8c .. 8c+7 lie inside chunks <= c: already consumed
+                    // 8 columns from this half's P start: they lie inside score chunks <= c of this half, already consumed
+                    tmem_st_32x32b_x8(ts + p_col0 + (c - c_lo) * 8, w8);
                 };
                 {
-                    uint32_t va[16], vb_[16];
-                    tmem_ld_32x32b_x16(ts, va);
-                    for (int c = 0; c < nchunk; c += 2) {
+                    uint32_t va[16];
+                    for (int c = c_lo; c < c_hi; ++c) {
+                        tmem_ld_32x32b_x16(ts + c * 16, va);
                         tmem_ld_wait();
-                        if (c + 1 < nchunk) tmem_ld_32x32b_x16(ts + (c + 1) * 16, vb_);
                         pass2(va, c);
-                        if (c + 1 < nchunk) {
-                            tmem_ld_wait();
-                            if (c + 2 < nchunk) tmem_ld_32x32b_x16(ts + (c + 2) * 16, va);
-                            pass2(vb_, c + 1);
-                        }
                     }
                 }
                 lsum = (ls0 + ls1) + (ls2 + ls3);
@@ -351,30 +379,34 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             tcgen05_fence_before();
             mbar_arrive(bar(PFULL0 + g));
             if (stamp) tp.dbg[n * 16 + 3] = clock64();
+            // row sum over both halves (exchanged while the P V product runs)
+            xch[(2 + hb) * kQRows + r] = lsum;
+            named_bar_sync(1 + g, 2 * kWgThreads);
+            lsum += xch[(2 + (hb ^ 1)) * kQRows + r];
             // ---- epilogue: O row * (dropout scale / l) -> bf16 -> four 32-byte stores ----
             mbar_wait(bar(OFULL0 + g), ph);
             tcgen05_fence_after();
             if (stamp) tp.dbg[n * 16 + 4] = clock64();
-            uint32_t o[4][16];
+            uint32_t o[2][16];   // this half's 32 of the 64 output columns
             if (wvalid) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) tmem_ld_32x32b_x16(tmem_o(g) + lane_sel + j * 16, o[j]);
+                for (int j = 0; j < 2; ++j) tmem_ld_32x32b_x16(tmem_o(g) + lane_sel + (hb * 2 + j) * 16, o[j]);
                 tmem_ld_wait();
             }
             tcgen05_fence_before();
             mbar_arrive(bar(OEMPTY0 + g));
             if (valid) {
                 const float inv = (drop ? p.drop_scale : 1.f) / lsum;
-                bf16* dst = p.ctx + (static_cast<long long>(b) * S + q) * p.H + h * kHd;
+                bf16* dst = p.ctx + (static_cast<long long>(b) * S + q) * p.H + h * kHd + hb * 32;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < 2; ++j) {
                     uint32_t w[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
                         w[i] = pack_bf16x2(__uint_as_float(o[j][2 * i]) * inv, __uint_as_float(o[j][2 * i + 1]) * inv);
                     stg_v8(dst + j * 16, w);
                 }
-                if (p.lse != nullptr) p.lse[static_cast<long long>(item) * S + q] = (m + log2f(lsum)) * 0.6931471805599453f;
+                if (hb == 0 && p.lse != nullptr) p.lse[static_cast<long long>(item) * S + q] = (m + log2f(lsum)) * 0.6931471805599453f;
             }
             if (stamp) tp.dbg[n * 16 + 5] = clock64();
         }
