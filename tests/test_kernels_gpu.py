@@ -266,3 +266,27 @@ def test_mlm_decoder_and_fused_cross_entropy(n, V):
     assert _rel(t.grad, tr.grad) < 2e-2
     assert _rel(E.grad, Er.grad) < 2e-2
     assert _rel(bias.grad, br.grad) < 2e-2
+
+
+def test_cross_entropy_ignores_out_of_range_labels():
+    """A label outside [0, V) (ignore indices such as -1 / -100, or >= V) contributes no loss and no gradient and is
+    never used as an index (the kernels used to read logits[label] unchecked)."""
+    from visualbert_b200 import ops
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    n, V = 12, 1000
+    Vp = (V + 15) // 16 * 16
+    base = torch.randn(n, Vp, device=dev).bfloat16()
+    labels = torch.randint(0, V, (n,), device=dev)
+    labels[1], labels[4], labels[7] = -100, V + 5, -1
+    valid = (labels >= 0) & (labels < V)
+    logits = base.clone().requires_grad_(True)
+    loss = ops.cross_entropy_rows(logits, labels, V)
+    loss.backward()
+    grad = logits.grad.float()
+    ref_in = base.float()[:, :V].requires_grad_(True)
+    rows = torch.nn.functional.cross_entropy(ref_in[valid], labels[valid], reduction="sum") / n  # mean over ALL rows given
+    rows.backward()
+    assert abs(loss.item() - rows.item()) < 2e-3 * abs(rows.item())
+    assert torch.all(grad[~valid] == 0)
+    assert _rel(grad[valid][:, :V], ref_in.grad[valid]) < 2e-2

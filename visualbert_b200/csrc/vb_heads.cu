@@ -67,7 +67,10 @@ ce_fwd_kernel(const bf16* __restrict__ logits, long long ld, const long long* __
     if (threadIdx.x == 0) {
         const float lse = gm + logf(gs);
         lse_out[row] = lse;
-        loss_out[row] = lse - __bfloat162float(x[labels[row]]);
+        // a label outside [0, vocab) (e.g. an ignore index) contributes no loss and, in ce_bwd_kernel, no gradient:
+        // never an out-of-bounds read
+        const long long lab = labels[row];
+        loss_out[row] = (lab >= 0 && lab < vocab) ? lse - __bfloat162float(x[lab]) : 0.f;
     }
 }
 
@@ -79,7 +82,9 @@ ce_bwd_kernel(bf16* __restrict__ logits, long long ld, const long long* __restri
     bf16* x = logits + row * ld;
     const float l2 = lse[row] * 1.4426950408889634f;
     const float scale = *scale_ptr;
-    const int label = static_cast<int>(labels[row]);
+    const long long lab = labels[row];
+    const bool ignored = lab < 0 || lab >= vocab;
+    const int label = ignored ? -1 : static_cast<int>(lab);
     const int chunks = padded >> 3;
     for (int ch = threadIdx.x; ch < chunks; ch += kCeThreads) {
         const uint4 u = *reinterpret_cast<const uint4*>(x + ch * 8);
@@ -88,7 +93,7 @@ ce_bwd_kernel(bf16* __restrict__ logits, long long ld, const long long* __restri
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int col = ch * 8 + i;
-            float g = col < vocab ? fast_ex2(fmaf(v[i], 1.4426950408889634f, -l2)) : 0.f;
+            float g = (col < vocab && !ignored) ? fast_ex2(fmaf(v[i], 1.4426950408889634f, -l2)) : 0.f;
             if (col == label) g -= 1.f;
             v[i] = g * scale;
         }

@@ -461,7 +461,9 @@ class BertVisualModel(PreTrainedBertModel):
         self.output_attention_weights = getattr(config, "output_attention_weights", False)
         self.apply(self.init_bert_weights)
         self._step = 0
-        self.dropout_seed = 0x5EED
+        # base of the counter-hash dropout streams: follows torch.manual_seed (so runs are reproducible the torch way);
+        # the data-parallel rank is mixed in per forward (next_seed) so replicas draw different masks
+        self.dropout_seed = (0x5EED ^ torch.initial_seed()) & 0xFFFFFFFF
 
     def _bank_sources(self):
         layers = list(self.encoder.layer) + ([self.additional_layer] if self.bypass_transformer else [])
@@ -516,7 +518,19 @@ class BertVisualModel(PreTrainedBertModel):
     def next_seed(self):
         """Per-forward dropout seed: forward and backward of one step share it; steps differ."""
         self._step += 1
-        return (self.dropout_seed * 0x9E3779B97F4A7C15 + self._step) & 0xFFFFFFFFFFFFFFFF
+        rank = 0
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            rank = torch.distributed.get_rank()
+        return ((self.dropout_seed + 0x632BE59B * rank) * 0x9E3779B97F4A7C15 + self._step) & 0xFFFFFFFFFFFFFFFF
+
+    def dropout_state(self):
+        """(base seed, forwards so far): save next to a checkpoint and hand back to set_dropout_state() to resume the
+        exact dropout sequence (kept out of state_dict so reference checkpoints still load with strict=True)."""
+        return {"seed": int(self.dropout_seed), "step": int(self._step)}
+
+    def set_dropout_state(self, state):
+        self.dropout_seed = int(state["seed"])
+        self._step = int(state["step"])
 
     def forward(self, input_ids, token_type_ids, attention_mask, visual_embeddings, position_embeddings_visual,
                 visual_embeddings_type, image_text_alignment, confidence, output_all_encoded_layers=True):
@@ -675,10 +689,13 @@ class TrainVisualBERTObjective(PreTrainedBertModel):
         self.apply(self.init_bert_weights)
 
     @staticmethod
-    def _labelled_rows(flat_labels):
+    def _labelled_rows(flat_labels, vocab=None):
         """Indices of the rows that carry an MLM target. `nonzero` synchronises with the device, so forward() calls this
-        BEFORE the encoder is enqueued (the stream is empty then) instead of draining ~12 ms of queued work later."""
-        return torch.nonzero(flat_labels.contiguous().view(-1) != -1).squeeze(1)
+        BEFORE the encoder is enqueued (the stream is empty then) instead of draining ~12 ms of queued work later.
+        Labels outside [0, vocab) are treated like the reference's ignore index -1 (CrossEntropyLoss(ignore_index=-1))."""
+        flat = flat_labels.contiguous().view(-1)
+        keep = flat >= 0 if vocab is None else (flat >= 0) & (flat < vocab)
+        return torch.nonzero(keep).squeeze(1)
 
     def _decoder_cache(self):
         """The tied decoder table rides the encoder's WeightBank (refreshed by the same launch, before the encoder runs)."""
@@ -708,7 +725,7 @@ class TrainVisualBERTObjective(PreTrainedBertModel):
         ignored rows contribute neither to the sum nor to the count, so value and gradients are unchanged."""
         labels = flat_labels.contiguous().view(-1)
         if rows is None:
-            rows = self._labelled_rows(flat_labels)
+            rows = self._labelled_rows(flat_labels, self.cls.predictions.decoder.weight.size(0))
         hidden = sequence_output.reshape(-1, sequence_output.size(-1)).index_select(0, rows)
         head = self.cls.predictions
         if rows.numel() == 0 or not hidden.is_cuda:
@@ -759,7 +776,7 @@ class TrainVisualBERTObjective(PreTrainedBertModel):
         mlm_rows = masked_lm_rows
         if (mlm_rows is None and self.training_head_type == "pretraining" and flat_masked_lm_labels is not None
                 and not output_all_encoded_layers):
-            mlm_rows = self._labelled_rows(flat_masked_lm_labels)  # the only host sync of the step: do it up front
+            mlm_rows = self._labelled_rows(flat_masked_lm_labels, self.cls.predictions.decoder.weight.size(0))  # the only host sync of the step: do it up front
         if self.output_attention_weights:
             # analysis mode (M.py:1430-1444): nothing but the per-layer attention maps is returned
             attention_weights = self.bert(

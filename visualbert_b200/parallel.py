@@ -130,7 +130,9 @@ class BatchPrefetcher:
     @staticmethod
     def labelled_rows(host_batch):
         """Flat indices b * (T + V) + t of the MLM targets, from the HOST copy of the labels (what
-        TrainVisualBERTObjective.forward accepts as `masked_lm_rows`): finding them on the device costs a host sync."""
+        TrainVisualBERTObjective.forward accepts as `masked_lm_rows`): finding them on the device costs a host sync.
+        Negative labels are "no target" (the reference's ignore index is -1); a label >= vocab contributes neither loss
+        nor gradient in the cross-entropy kernels."""
         labels = host_batch.get("masked_lm_labels")
         if labels is None or labels.is_cuda:
             return None
@@ -138,7 +140,7 @@ class BatchPrefetcher:
         T = labels.shape[-1]
         V = 0 if vis is None else vis.shape[-2]
         flat = labels.reshape(-1, T)
-        b, t = torch.nonzero(flat != -1, as_tuple=True)
+        b, t = torch.nonzero(flat >= 0, as_tuple=True)
         return (b * (T + V) + t).to(torch.int64)
 
     def stage(self, host_batch):
