@@ -311,7 +311,7 @@ def test_data_updating_optimizer_is_seen_by_the_compute_weights():
     fresh = TrainVisualBERTObjective(BertConfig.from_dict(cfg), c["head"], visual_embedding_dim=c["Dv"], **c.get("flags", {}))
     fresh.load_state_dict(model.state_dict(), strict=False)
     fresh.to(l0.device).train()
-    fresh.bert._step = 100
+    fresh.bert.set_dropout_state(dict(model.bert.dropout_state(), step=100))
     l2 = fresh(**batch)["loss"].item()
     assert abs(l1 - l2) <= 1e-5 * abs(l2) + 1e-6
     # eval mode keeps the cache until a version changes
