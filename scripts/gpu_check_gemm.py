@@ -125,6 +125,8 @@ def run_case(name):
             "qkv_bias": (41984, 2304, 768, {"bias": True}),
             "ffn_down": (41984, 768, 3072, {}),
             "dgrad_ffn_up": (41984, 768, 3072, {"dgrad": True}),
+            "dgrad_ffn_down_dgelu": (41984, 3072, 768, {"dgrad": True, "dgelu": True}),
+            "dgrad_qkv_accum": (41984, 768, 2304, {"dgrad": True, "add": True}),
             "wgrad_ffn_up": (3072, 768, 41984, {"wgrad": True}),
             "wgrad_attn_out": (768, 768, 41984, {"wgrad": True}),
         }.items():
@@ -139,6 +141,12 @@ def run_case(name):
                 A = rnd(M, K); B = rnd(K, N)
                 D = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
                 args = dict(A=A.data_ptr(), lda=K, B=B.data_ptr(), ldb=N, b_mn_major=1, M=M, N=N, K=K, D=D.data_ptr(), ldd=N)
+                if kw.get("dgelu"):
+                    U = rnd(M, N)
+                    args.update(epilogue=_lib.VB_EPI_DGELU, aux_in=U.data_ptr(), ld_aux=N)
+                if kw.get("add"):
+                    R = rnd(M, N)
+                    args.update(addend=R.data_ptr(), ld_add=N)
             else:
                 A = rnd(M, K); B = rnd(N, K)
                 D = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)

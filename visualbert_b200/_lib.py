@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libvbert_b200.so")
+# VB_LIB_PATH: load another build of the same library (A/B timing of kernel variants on one GPU box, scripts/build_variant.sh)
+LIB_PATH = os.environ.get("VB_LIB_PATH") or os.path.join(_HERE, "lib", "libvbert_b200.so")
 
 VB_EPI_NONE, VB_EPI_GELU, VB_EPI_DGELU = 0, 1, 2
 

@@ -391,6 +391,19 @@ __device__ __forceinline__ void umma_commit_2cta(uint32_t bar, uint32_t cta_mask
                  "h"(static_cast<uint16_t>(cta_mask))
                  : "memory");
 }
+// TMA store of one box from (swizzled) shared memory; completion is tracked per thread in bulk async-groups
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c_inner, int c_outer) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c_inner), "r"(c_outer)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the issuing thread's bulk groups have finished READING shared memory (the source may be overwritten)
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void sts_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 // TMA load multicast to the CTAs of `cta_mask`: the box lands at the same CTA-relative offset in each of them and the
 // bytes are credited to the barrier at this offset in the LEADER of each destination CTA's pair (peer bit cleared)
 __device__ __forceinline__ void tma_load_2d_2cta_mc(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c_inner, int c_outer,

@@ -168,9 +168,11 @@ __device__ __forceinline__ void store16_bf16(bf16* p, const float (&f)[16]) {
 // `no_instruction` stalls of 0.5-2.4 warps per issue cycle on the epilogue-bound launches. A specialised kernel carries only its path.
 enum { EPI_GENERIC = 0, EPI_BIAS = 1, EPI_RESID = 2, EPI_DROP_RESID = 3, EPI_GELU_FWD = 4, EPI_DGELU_BWD = 5 };
 
-template <bool OUT_F32, int EPI = EPI_GENERIC>
+// TO_REGS: nothing is stored; the 16 bf16 results are returned packed in o0 (what goes to D) and, for the GELU epilogue,
+// o1 (what goes to aux_out) — the caller stages them in shared memory for a TMA store.
+template <bool OUT_F32, int EPI = EPI_GENERIC, bool TO_REGS = false>
 __device__ __forceinline__ void epilogue16(const GemmParams& p, int row, int col, const float* sbias, const uint32_t (&ex)[8],
-                                           float (&x)[16]) {
+                                           float (&x)[16], uint32_t* o0 = nullptr, uint32_t* o1 = nullptr) {
     if (sbias != nullptr) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -208,6 +210,11 @@ __device__ __forceinline__ void epilogue16(const GemmParams& p, int row, int col
             float gp[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) gelu_fwd_bwd(x[i], x[i], gp[i]);
+            if constexpr (TO_REGS) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { o0[i] = pack_bf16x2(gp[2 * i], gp[2 * i + 1]); o1[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]); }
+                return;
+            }
             store16_bf16(d, gp);
             d = p.aux_out + static_cast<long long>(row) * p.ld_aux + col;
         } else if (kGeneric && p.epilogue == 3) {  // debug/tuning only: two stores, no GELU math
@@ -220,6 +227,11 @@ __device__ __forceinline__ void epilogue16(const GemmParams& p, int row, int col
                 x[2 * i] *= t.x;
                 x[2 * i + 1] *= t.y;
             }
+        }
+        if constexpr (TO_REGS) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o0[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
+            return;
         }
         store16_bf16(d, x);
     }
@@ -431,19 +443,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 //   empty[s], tmem_full[a]  live in both CTAs, arrived by the leader's multicast tcgen05.commit
 //   tmem_empty[a]           lives in the leader: 2 x 256 epilogue-thread arrivals (peer arrives remotely)
 // ---------------------------------------------------------------------------------------------
-constexpr int kStages2 = 6;
-struct Cfg2 {
+#ifndef VB_GEMM_DEEP_EX
+#define VB_GEMM_DEEP_EX 1   // 0: ring of four operand buffers instead of the whole tile row (A/B timing, scripts/build_variant.sh)
+#endif
+// TMA_ST: the epilogue stages its bf16 output in shared memory (one private 32-row x 64-column swizzled slab per epilogue
+// warp) and writes it with TMA stores. A thread owns a ROW of the tile, so direct global stores are 32 separate 32-byte
+// sectors per warp instruction; measured (scripts/gpu_check_gemm.py perf) every such scattered sector costs ~3 cycles of
+// the SM's load/store path — 12.7 k cycles per tile for the two outputs of the GELU epilogue against 9 k for the tile's
+// main loop. The slabs take the room of one pipeline stage (5 instead of 6).
+template <bool TMA_ST>
+struct Cfg2T {
+    static constexpr int kStages2 = TMA_ST ? 5 : 6;
+    static constexpr int STAGING_BYTES = TMA_ST ? kEpiWarps * 4096 : 0;
     static constexpr int BLOCK_N = 256;
     static constexpr int A_BYTES = 128 * BLOCK_K * 2;       // this CTA's 128 rows of A
     static constexpr int B_BYTES = 128 * BLOCK_K * 2;       // this CTA's half of the 256 B rows
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BAR_OFF = kStages2 * STAGE_BYTES;
+    static constexpr int STAGING_OFF = kStages2 * STAGE_BYTES;  // 1 KB aligned (stages are 32 KB)
+    static constexpr int BAR_OFF = STAGING_OFF + STAGING_BYTES;
     static constexpr int NUM_BARS = 2 * kStages2 + 4;
     static constexpr int TMEM_PTR_OFF = BAR_OFF + NUM_BARS * 8;
     static constexpr int BIAS_OFF = TMEM_PTR_OFF + 16;
     static constexpr int SMEM_BYTES = BIAS_OFF + 2 * BLOCK_N * 4 + 1024;
     static constexpr int TMEM_COLS = 512;
 };
+using Cfg2 = Cfg2T<false>;
 
 __host__ __device__ constexpr uint32_t make_idesc_m(int m, int n, bool a_mn, bool b_mn) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn) << 15) |
@@ -456,11 +480,14 @@ __host__ __device__ constexpr uint32_t make_idesc_m(int m, int n, bool a_mn, boo
 // in the other pair, so the L2 -> SM operand traffic per pair and k-block drops from 64 KB to 48 KB. (These GEMMs run at
 // the L2 bandwidth limit — see DESIGN.md — which is why this matters.) A stage may only be refilled once BOTH pairs have
 // consumed it (the other pair writes into it too): empty[s] counts one commit from each pair.
-template <bool A_MN, bool B_MN, bool OUT_F32, int EPI, int CL = 2>
+template <bool A_MN, bool B_MN, bool OUT_F32, int EPI, int CL = 2, bool TMA_ST = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const GemmParams p) {
-    using C = Cfg2;
+                         const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
+    constexpr bool kTmaSt = TMA_ST;
+    static_assert(!TMA_ST || (!OUT_F32 && EPI != EPI_GENERIC), "staged stores: bf16 outputs of the specialised epilogues");
+    using C = Cfg2T<kTmaSt>;
+    constexpr int kStages2 = C::kStages2;
     constexpr int BLOCK_N = 256;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -524,7 +551,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
     // Epilogues that read a second operand (residual / gelu') hold the whole tile row of it in registers (see below): the
     // four control warps hand registers to the eight epilogue warps (128 * 72 + 256 * 216 = 384 * 168).
-    constexpr bool kDeepEx = !OUT_F32 && (EPI == EPI_RESID || EPI == EPI_DROP_RESID || EPI == EPI_DGELU_BWD);
+    constexpr bool kDeepEx = VB_GEMM_DEEP_EX && !OUT_F32 && (EPI == EPI_RESID || EPI == EPI_DROP_RESID || EPI == EPI_DGELU_BWD);
     if (warp == 0) {
         if constexpr (kDeepEx) reg_dec<72>();
         {
@@ -629,8 +656,25 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 }
                 named_bar_sync(1, kEpiWarps * 32);
             }
-            const int row = tc.m_blk * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;
+            const int row0w = tc.m_blk * 256 + static_cast<int>(rank) * 128 + q * 32;  // first of this warp's 32 rows
+            const int row = row0w + lane;
             const int col0 = tc.n_blk * BLOCK_N + half * (BLOCK_N / 2);
+            // staged TMA store (kTmaSt): this warp's private slab, 32 rows x 128 bytes, 128-byte swizzle
+            const uint32_t slab = base + C::STAGING_OFF + ew * 4096;
+            auto stage16 = [&](int kk, const uint32_t (&o)[8]) {  // 16 columns = 16-byte units 2kk, 2kk + 1 of this thread's row
+                const uint32_t rowa = slab + lane * 128, sw = static_cast<uint32_t>(lane & 7);
+                sts_v4(rowa + ((2u * kk) ^ sw) * 16, o[0], o[1], o[2], o[3]);
+                sts_v4(rowa + ((2u * kk + 1u) ^ sw) * 16, o[4], o[5], o[6], o[7]);
+            };
+            auto slab_free = [&]() {  // the previous store of this warp has read the slab
+                if (lane == 0) bulk_wait_group_read0();
+                __syncwarp();
+            };
+            auto flush = [&](const CUtensorMap* tm, int c0) {  // rows / columns beyond M / N are clipped by the TMA unit
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) { tma_store_2d(tm, slab, c0, row0w); bulk_commit_group(); }
+            };
             constexpr int kExAhead = 4;
             const bf16* exp_ = nullptr;
             if constexpr (!OUT_F32) {
@@ -665,16 +709,24 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                         tmem_ld_wait();
                         if (k + 1 < NCH) tmem_ld_32x32b_x16(taddr0 + (k + 1) * 16, v[(kk + 1) & 1]);
                         const int col = col0 + k * 16;
-                        if (row < p.M && col < p.N) {
+                        if (kTmaSt || (row < p.M && col < p.N)) {
                             float x[16];
                             uint32_t e[8];
 #pragma unroll
                             for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[kk & 1][i]);
 #pragma unroll
                             for (int i = 0; i < 8; ++i) e[i] = k0 ? exB[kk][i] : exA[kk][i];
-                            epilogue16<OUT_F32, EPI>(p, row, col, has_bias ? sb + half * (BLOCK_N / 2) + k * 16 : nullptr, e, x);
+                            if constexpr (kTmaSt) {
+                                uint32_t o0[8];
+                                epilogue16<OUT_F32, EPI, true>(p, row, col, has_bias ? sb + half * (BLOCK_N / 2) + k * 16 : nullptr, e, x, o0);
+                                if (kk == 0) slab_free();
+                                stage16(kk, o0);
+                            } else {
+                                epilogue16<OUT_F32, EPI>(p, row, col, has_bias ? sb + half * (BLOCK_N / 2) + k * 16 : nullptr, e, x);
+                            }
                         }
                     }
+                    if constexpr (kTmaSt) flush(&tmD, col0 + k0 * 16);
                 }
             } else {
                 // Residual / gelu' operand of this thread's row (generic kernel): one 32-byte load per 16-column chunk,
@@ -688,8 +740,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 tmem_ld_32x32b_x16(taddr0, v[0]);
                 // chunks in groups: inside a group every buffer index is static; the group loop is NOT unrolled (code size)
                 // (epilogues without a prefetched operand only need the 2-deep TMEM double buffer: groups of 2 halve their code again)
-                constexpr int kGroup = (EPI == EPI_GELU_FWD || EPI == EPI_BIAS) ? 2 : kExAhead;
+                constexpr int kGroup = (!kTmaSt && (EPI == EPI_GELU_FWD || EPI == EPI_BIAS)) ? 2 : kExAhead;  // staged stores: one slab = 4 chunks
                 static_assert(NCH % kGroup == 0, "chunk groups");
+                uint32_t gk[kTmaSt && EPI == EPI_GELU_FWD ? kGroup : 1][8];  // gelu(u) of the slab, stored after gelu'(u)
 #pragma unroll 1
                 for (int k0 = 0; k0 < NCH; k0 += kGroup) {
 #pragma unroll
@@ -698,21 +751,42 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                         tmem_ld_wait();
                         if (k + 1 < NCH) tmem_ld_32x32b_x16(taddr0 + (k + 1) * 16, v[(kk + 1) & 1]);
                         const int col = col0 + k * 16;
-                        if (row < p.M && col < p.N) {
+                        if (kTmaSt || (row < p.M && col < p.N)) {
                             float x[16];
 #pragma unroll
                             for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[kk & 1][i]);
-                            epilogue16<OUT_F32, EPI>(p, row, col, has_bias ? sb + half * (BLOCK_N / 2) + k * 16 : nullptr, ex[kk], x);
+                            if constexpr (kTmaSt) {
+                                uint32_t o0[8];
+                                epilogue16<OUT_F32, EPI, true>(p, row, col, has_bias ? sb + half * (BLOCK_N / 2) + k * 16 : nullptr, ex[kk], x, o0,
+                                                               gk[EPI == EPI_GELU_FWD ? kk : 0]);
+                                if (kk == 0) slab_free();
+                                stage16(kk, o0);
+                            } else {
+                                epilogue16<OUT_F32, EPI>(p, row, col, has_bias ? sb + half * (BLOCK_N / 2) + k * 16 : nullptr, ex[kk], x);
+                            }
                         }
                         // buffer kk is free again: refill it with the operand of chunk k + kExAhead
                         if (k + kExAhead < NCH && exp_ != nullptr && col0 + (k + kExAhead) * 16 < p.N)
                             ldg_v8(exp_ + col0 + (k + kExAhead) * 16, ex[kk]);
+                    }
+                    if constexpr (kTmaSt) {
+                        flush(&tmD, col0 + k0 * 16);
+                        if constexpr (EPI == EPI_GELU_FWD) {
+                            slab_free();
+#pragma unroll
+                            for (int kk = 0; kk < kGroup; ++kk) stage16(kk, gk[kk]);
+                            flush(&tmAux, col0 + k0 * 16);
+                        }
                     }
                 }
             }
             tcgen05_fence_before();
             if (leader) mbar_arrive(tempty_bar(acc));
             else mbar_arrive_remote(tempty_bar(acc), leader_rank);
+        }
+        if constexpr (kTmaSt) {
+            if (lane == 0) bulk_wait_group0();   // the staged stores have left shared memory and are complete before the CTA exits
+            __syncwarp();
         }
     } else {
         if constexpr (kDeepEx) reg_dec<72>();   // warps 2 and 3 release their share as well (the pool is per CTA)
@@ -844,17 +918,20 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
     return 0;
 }
 
-template <bool A_MN, bool B_MN, bool OUT_F32, int EPI = EPI_GENERIC>
-static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-    auto kern = gemm_tcgen05_2cta_kernel<A_MN, B_MN, OUT_F32, EPI>;
+// td / tx: tensor maps of D and aux_out for the staged TMA stores (unused by kernels that store from registers)
+template <bool A_MN, bool B_MN, bool OUT_F32, int EPI = EPI_GENERIC, bool TMA_ST = false>
+static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tx, const GemmParams& p,
+                   cudaStream_t st) {
+    auto kern = gemm_tcgen05_2cta_kernel<A_MN, B_MN, OUT_F32, EPI, 2, TMA_ST>;
+    using C = Cfg2T<TMA_ST>;
     static int configured[kMaxDevices] = {0};
-    VB_CHECK_CUDA(ensure_dyn_smem(kern, Cfg2::SMEM_BYTES, configured));
+    VB_CHECK_CUDA(ensure_dyn_smem(kern, C::SMEM_BYTES, configured));
     const int tiles = ((p.M + 255) / 256) * ((p.N + 255) / 256) * p.splits;
     int clusters = num_sms() / 2;
     if (clusters > tiles) clusters = tiles;
     {
         ProfScope ps(st, OUT_F32 ? PROF_GEMM_WGRAD : (B_MN ? PROF_GEMM_DGRAD : PROF_GEMM_FWD), 2.0 * p.M * p.N * p.K, 1);
-        VB_CHECK_CUDA(launch_pdl_cluster(kern, dim3(2 * clusters), dim3(kThreads), Cfg2::SMEM_BYTES, st, 2, ta, tb, p));
+        VB_CHECK_CUDA(launch_pdl_cluster(kern, dim3(2 * clusters), dim3(kThreads), C::SMEM_BYTES, st, 2, ta, tb, td, tx, p));
     }
     VB_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -863,7 +940,8 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
 // Quad variant (two CTA pairs per cluster sharing the B tile by TMA multicast). Returns -1 when clusters of four cannot be
 // placed on this device (the caller then uses the pair kernel).
 template <bool B_MN, int EPI>
-static int launch4(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+static int launch4(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tx, const GemmParams& p,
+                   cudaStream_t st) {
     auto kern = gemm_tcgen05_2cta_kernel<false, B_MN, false, EPI, 4>;
     static int configured[kMaxDevices] = {0};
     static int resident[kMaxDevices] = {0};  // clusters of four that fit on the device at once (0 = not asked yet)
@@ -890,7 +968,8 @@ static int launch4(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
     if (clusters > tiles) clusters = tiles;
     {
         ProfScope ps(st, B_MN ? PROF_GEMM_DGRAD : PROF_GEMM_FWD, 2.0 * p.M * p.N * p.K, 1);
-        VB_CHECK_CUDA(launch_pdl_cluster(kern, dim3(4 * clusters), dim3(kThreads), Cfg2::SMEM_BYTES, st, 4, ta, tb, p));
+        (void)td; (void)tx;
+        VB_CHECK_CUDA(launch_pdl_cluster(kern, dim3(4 * clusters), dim3(kThreads), Cfg2::SMEM_BYTES, st, 4, ta, tb, ta, ta, p));
     }
     VB_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -980,6 +1059,24 @@ int gemm(const vb_gemm_args& a, cudaStream_t st) {
             if (a.epilogue == VB_EPI_GELU && !drop && !add) epi = EPI_GELU_FWD;
             else if (a.epilogue == VB_EPI_DGELU && !drop && !add) epi = EPI_DGELU_BWD;
             else if (a.epilogue == VB_EPI_NONE) epi = add ? (drop ? EPI_DROP_RESID : EPI_RESID) : (drop ? EPI_GENERIC : EPI_BIAS);
+            // Staged TMA stores where the epilogue, not the main loop, bounds the tile (measured r02, same box, us per
+            // launch with / without: FFN-up + GELU 200 / 214, attention-output 59 / 66, but K = 3072 or bias-only epilogues
+            // 3-4 us SLOWER — the slabs cost a pipeline stage). VB_GEMM_TMA_STORE=0 / 1 forces never / wherever possible.
+            static const int tma_mode = [] { const char* e = getenv("VB_GEMM_TMA_STORE"); return e ? atoi(e) : 2; }();
+            bool tma_st = false;
+            if (tma_mode == 1) tma_st = epi != EPI_GENERIC;
+            else if (tma_mode != 0)
+                tma_st = epi == EPI_GELU_FWD || epi == EPI_DGELU_BWD || ((epi == EPI_RESID || epi == EPI_DROP_RESID) && a.K <= 1536);
+            // output tensor maps for the staged TMA stores: 64-column x 32-row boxes (one epilogue warp's slab)
+            CUtensorMap td = ta, tx = ta;
+            if (tma_st) {
+                rc = make_tmap_bf16(&td, a.D, a.N, a.M, a.ldd, 32);
+                if (rc) return rc;
+                if (epi == EPI_GELU_FWD) {
+                    rc = make_tmap_bf16(&tx, a.aux_out, a.N, a.M, a.ld_aux, 32);
+                    if (rc) return rc;
+                }
+            }
             // quad clusters for the tall activation GEMMs of the layer (at least two 256-row blocks to pair up)
             if (use_quad() && epi != EPI_GENERIC && !a.a_mn_major && a.M > 256) {
                 CUtensorMap tq;  // K-major B is fetched in 64-row boxes (half of a CTA's part), MN-major B already is
@@ -988,17 +1085,17 @@ int gemm(const vb_gemm_args& a, cudaStream_t st) {
                     rc = make_tmap_bf16(&tq, a.B, a.K, a.N, a.ldb, 64);
                     if (rc) return rc;
                     switch (epi) {
-                        case EPI_BIAS: q = launch4<false, EPI_BIAS>(ta, tq, p, st); break;
-                        case EPI_RESID: q = launch4<false, EPI_RESID>(ta, tq, p, st); break;
-                        case EPI_DROP_RESID: q = launch4<false, EPI_DROP_RESID>(ta, tq, p, st); break;
-                        case EPI_GELU_FWD: q = launch4<false, EPI_GELU_FWD>(ta, tq, p, st); break;
+                        case EPI_BIAS: q = launch4<false, EPI_BIAS>(ta, tq, td, tx, p, st); break;
+                        case EPI_RESID: q = launch4<false, EPI_RESID>(ta, tq, td, tx, p, st); break;
+                        case EPI_DROP_RESID: q = launch4<false, EPI_DROP_RESID>(ta, tq, td, tx, p, st); break;
+                        case EPI_GELU_FWD: q = launch4<false, EPI_GELU_FWD>(ta, tq, td, tx, p, st); break;
                         default: q = -1; break;
                     }
                 } else {
                     switch (epi) {
-                        case EPI_BIAS: q = launch4<true, EPI_BIAS>(ta, tb, p, st); break;
-                        case EPI_RESID: q = launch4<true, EPI_RESID>(ta, tb, p, st); break;
-                        case EPI_DGELU_BWD: q = launch4<true, EPI_DGELU_BWD>(ta, tb, p, st); break;
+                        case EPI_BIAS: q = launch4<true, EPI_BIAS>(ta, tb, td, tx, p, st); break;
+                        case EPI_RESID: q = launch4<true, EPI_RESID>(ta, tb, td, tx, p, st); break;
+                        case EPI_DGELU_BWD: q = launch4<true, EPI_DGELU_BWD>(ta, tb, td, tx, p, st); break;
                         default: q = -1; break;
                     }
                 }
@@ -1006,28 +1103,28 @@ int gemm(const vb_gemm_args& a, cudaStream_t st) {
             }
             if (!a.a_mn_major && !a.b_mn_major) {
                 switch (epi) {
-                    case EPI_BIAS: return launch2<false, false, false, EPI_BIAS>(ta, tb, p, st);
-                    case EPI_RESID: return launch2<false, false, false, EPI_RESID>(ta, tb, p, st);
-                    case EPI_DROP_RESID: return launch2<false, false, false, EPI_DROP_RESID>(ta, tb, p, st);
-                    case EPI_GELU_FWD: return launch2<false, false, false, EPI_GELU_FWD>(ta, tb, p, st);
-                    default: return launch2<false, false, false>(ta, tb, p, st);
+                    case EPI_BIAS: return (tma_st ? launch2<false, false, false, EPI_BIAS, true>(ta, tb, td, tx, p, st) : launch2<false, false, false, EPI_BIAS, false>(ta, tb, td, tx, p, st));
+                    case EPI_RESID: return (tma_st ? launch2<false, false, false, EPI_RESID, true>(ta, tb, td, tx, p, st) : launch2<false, false, false, EPI_RESID, false>(ta, tb, td, tx, p, st));
+                    case EPI_DROP_RESID: return (tma_st ? launch2<false, false, false, EPI_DROP_RESID, true>(ta, tb, td, tx, p, st) : launch2<false, false, false, EPI_DROP_RESID, false>(ta, tb, td, tx, p, st));
+                    case EPI_GELU_FWD: return (tma_st ? launch2<false, false, false, EPI_GELU_FWD, true>(ta, tb, td, tx, p, st) : launch2<false, false, false, EPI_GELU_FWD, false>(ta, tb, td, tx, p, st));
+                    default: return launch2<false, false, false>(ta, tb, ta, ta, p, st);
                 }
             }
             if (!a.a_mn_major && a.b_mn_major) {
                 switch (epi) {
-                    case EPI_BIAS: return launch2<false, true, false, EPI_BIAS>(ta, tb, p, st);
-                    case EPI_RESID: return launch2<false, true, false, EPI_RESID>(ta, tb, p, st);
-                    case EPI_DGELU_BWD: return launch2<false, true, false, EPI_DGELU_BWD>(ta, tb, p, st);
-                    default: return launch2<false, true, false>(ta, tb, p, st);
+                    case EPI_BIAS: return (tma_st ? launch2<false, true, false, EPI_BIAS, true>(ta, tb, td, tx, p, st) : launch2<false, true, false, EPI_BIAS, false>(ta, tb, td, tx, p, st));
+                    case EPI_RESID: return (tma_st ? launch2<false, true, false, EPI_RESID, true>(ta, tb, td, tx, p, st) : launch2<false, true, false, EPI_RESID, false>(ta, tb, td, tx, p, st));
+                    case EPI_DGELU_BWD: return (tma_st ? launch2<false, true, false, EPI_DGELU_BWD, true>(ta, tb, td, tx, p, st) : launch2<false, true, false, EPI_DGELU_BWD, false>(ta, tb, td, tx, p, st));
+                    default: return launch2<false, true, false>(ta, tb, ta, ta, p, st);
                 }
             }
-            if (a.a_mn_major && a.b_mn_major) return launch2<true, true, false>(ta, tb, p, st);
-            return launch2<true, false, false>(ta, tb, p, st);
+            if (a.a_mn_major && a.b_mn_major) return launch2<true, true, false>(ta, tb, ta, ta, p, st);
+            return launch2<true, false, false>(ta, tb, ta, ta, p, st);
         } else {
-            if (!a.a_mn_major && !a.b_mn_major) return launch2<false, false, true>(ta, tb, p, st);
-            if (!a.a_mn_major && a.b_mn_major) return launch2<false, true, true>(ta, tb, p, st);
-            if (a.a_mn_major && a.b_mn_major) return launch2<true, true, true>(ta, tb, p, st);
-            return launch2<true, false, true>(ta, tb, p, st);
+            if (!a.a_mn_major && !a.b_mn_major) return launch2<false, false, true>(ta, tb, ta, ta, p, st);
+            if (!a.a_mn_major && a.b_mn_major) return launch2<false, true, true>(ta, tb, ta, ta, p, st);
+            if (a.a_mn_major && a.b_mn_major) return launch2<true, true, true>(ta, tb, ta, ta, p, st);
+            return launch2<true, false, true>(ta, tb, ta, ta, p, st);
         }
     }
     if (!a.a_mn_major) rc = make_tmap_bf16(&ta, a.A, a.K, a.M, a.lda, BLOCK_M);
