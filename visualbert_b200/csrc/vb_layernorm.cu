@@ -14,6 +14,7 @@ namespace vb {
 
 constexpr int kLnWarps = 8;
 
+// (two rows per warp, both requested up front, measured SLOWER in-step: 0.965 vs 0.905 ms per step, r02)
 template <int NC>
 __global__ void __launch_bounds__(kLnWarps * 32)
 ln_fwd_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__ gamma,
@@ -123,20 +124,31 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
     __syncthreads();
 
     const float invH = 1.0f / H;
-    for (int row = blockIdx.x * kLnWarps + warp; row < rows; row += gridDim.x * kLnWarps) {
-        const long long rbase = static_cast<long long>(row) * H;
-        const unsigned long long e8row = static_cast<unsigned long long>(row) * static_cast<unsigned>(chunks);
-        uint4 ux[NC], ud[NC];
+    // The packed row (ux, ud) is dead once it is unpacked to fp32: the NEXT row of this warp is requested right there, so its
+    // 3 KB travel under the two passes over the current row (before: loads and arithmetic alternated, ~48 KB in flight per SM).
+    const int rstride = gridDim.x * kLnWarps;
+    int row = blockIdx.x * kLnWarps + warp;
+    uint4 ux[NC], ud[NC];
+    float mu = 0.f, rs = 0.f;
+    auto request = [&](int rw) {
+        const long long rb = static_cast<long long>(rw) * H;
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             const int ch = lane + c * 32;
             if (ch < chunks) {
-                ux[c] = ldg_v4(x + rbase + ch * 8);
-                ud[c] = ldg_v4(dy + rbase + ch * 8);
+                ux[c] = ldg_v4(x + rb + ch * 8);
+                ud[c] = ldg_v4(dy + rb + ch * 8);
             }
         }
-        const float mu = mean[row], rs = rstd[row];
+        mu = mean[rw];
+        rs = rstd[rw];
+    };
+    if (row < rows) request(row);
+    for (; row < rows; row += rstride) {
+        const long long rbase = static_cast<long long>(row) * H;
+        const unsigned long long e8row = static_cast<unsigned long long>(row) * static_cast<unsigned>(chunks);
         const float nmr = -mu * rs;
+        const float rs_cur = rs;
         // the row is unpacked ONCE: xh = xhat and dv = dy stay in fp32 registers for both passes (the kernel is
         // instruction-issue bound, not register/occupancy bound: profiles/r01final_layer_kernels.md)
         float xh[NC][8], dv[NC][8];
@@ -147,6 +159,13 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
             if (ch < chunks) {
                 unpack8(ux[c], xh[c]);
                 unpack8(ud[c], dv[c]);
+            }
+        }
+        if (row + rstride < rows) request(row + rstride);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const int ch = lane + c * 32;
+            if (ch < chunks) {
                 if (in_scale != 0.f) {  // dy is the gradient of dropout(LN(x)): re-apply the keep mask
                     const uint32_t keep = dropout_keep8(drop_seed, in_stream, e8row + ch, in_thresh16);
 #pragma unroll
@@ -156,7 +175,7 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
                 const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    xh[c][i] = fmaf(xh[c][i], rs, nmr);  // xhat
+                    xh[c][i] = fmaf(xh[c][i], rs_cur, nmr);  // xhat
                     const float g = dv[c][i] * gm[i];
                     s1 += g;
                     s2 = fmaf(g, xh[c][i], s2);
@@ -164,7 +183,7 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
             }
         }
         const float c1 = warp_sum(s1) * invH, c2 = warp_sum(s2) * invH;
-        const float rc1 = rs * c1, rc2 = rs * c2;
+        const float rc1 = rs_cur * c1, rc2 = rs_cur * c2;
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             const int ch = lane + c * 32;
@@ -174,7 +193,7 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
                 float o[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i)  // rs * (g - c1 - xhat * c2)
-                    o[i] = fmaf(-xh[c][i], rc2, fmaf(dv[c][i] * gm[i], rs, -rc1));
+                    o[i] = fmaf(-xh[c][i], rc2, fmaf(dv[c][i] * gm[i], rs_cur, -rc1));
                 stg_v4(dx + rbase + ch * 8, pack8(o));
                 if (dx_drop != nullptr) {
                     const uint32_t keep = dropout_keep8(drop_seed, drop_stream, e8row + ch, drop_thresh16);
