@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VB_ABI_VERSION 1
+#define VB_ABI_VERSION 2
 
 /* ---- library ---------------------------------------------------------------------------- */
 int vb_abi_version(void);
@@ -66,7 +66,18 @@ typedef struct {
     int64_t ld_aux;
     /* inverted dropout on (acc + bias) before the addend — M.py:272, 317 (nn.Dropout) */
     float dropout_p; uint64_t dropout_seed; uint32_t dropout_stream;
+    /* gp_tiled = 1 (VB_EPI_GELU / VB_EPI_DGELU only, and only when vb_gemm_gp_tiled_ok(M, N)): gelu'(u) — D of the GELU
+     * epilogue, aux_in of the DGELU epilogue — is kept in the library's TILE-NATIVE order instead of row-major [M, N]:
+     * same M * N bf16 elements; for the 256 x 256 tile (mb, nb), CTA rank r (rows 128 r ..), epilogue warp w = 4 * column-half +
+     * row-quarter, 16-column chunk k, lane l: the 16 elements of row 256 mb + 128 r + 32 (w % 4) + l, columns
+     * 256 nb + 128 (w / 4) + 16 k .. + 15 sit at element ((((mb * N/256 + nb) * 2 + r) * 8 + w) * 8 + k) * 512 + 16 l.
+     * The tensor has exactly one producer and one consumer — two GEMM epilogues in which the same thread owns the same
+     * 16 columns — so both touch whole 1 KB warp blocks instead of 32-byte pieces of 32 rows. vb_layer_fwd / _bwd use it
+     * for vb_layer_acts.u whenever the shape allows. */
+    int32_t gp_tiled;
 } vb_gemm_args;
+/* 1 when gp_tiled is supported for this output shape on this build (M, N multiples of 256, CTA-pair kernels enabled) */
+int vb_gemm_gp_tiled_ok(int32_t M, int32_t N);
 
 int vb_gemm(const vb_gemm_args* args, void* stream);
 
@@ -159,7 +170,8 @@ typedef struct {
     void* pre1;  /* [M, H]  attention.output.dense(ctx) (+dropout) + x          (M.py:271-273 before LN) */
     float* mean1; float* rstd1; /* [M] fp32 */
     void* x1;    /* [M, H]  attention output = LN(pre1) */
-    void* u;     /* [M, I]  gelu'(u), u = intermediate.dense(x1) — the derivative is what backward needs */
+    void* u;     /* M * I bf16: gelu'(u), u = intermediate.dense(x1) — the derivative is what backward needs. Private to the
+                    library (row-major [M, I], or tile-native when vb_gemm_gp_tiled_ok(M, I): see vb_gemm_args.gp_tiled) */
     void* g;     /* [M, I]  gelu(u) */
     void* pre2;  /* [M, H]  output.dense(g) (+dropout) + x1                      (M.py:316-318 before LN) */
     float* mean2; float* rstd2;

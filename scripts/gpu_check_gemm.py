@@ -116,6 +116,7 @@ def run_case(name):
         for tag, (M, N, K, kw) in {
             "qkv_fwd": (41984, 2304, 768, {}),
             "ffn_up_gelu": (41984, 3072, 768, {"gelu": True}),
+            "ffn_up_gelu_tiled": (41984, 3072, 768, {"gelu": True, "tiled": True}),
             "ffn_up_dual_nomath": (41984, 3072, 768, {"gelu": True, "epi": 3}),
             "ffn_up_plain": (41984, 3072, 768, {}),
             "attn_out_plain": (41984, 768, 768, {}),
@@ -126,6 +127,7 @@ def run_case(name):
             "ffn_down": (41984, 768, 3072, {}),
             "dgrad_ffn_up": (41984, 768, 3072, {"dgrad": True}),
             "dgrad_ffn_down_dgelu": (41984, 3072, 768, {"dgrad": True, "dgelu": True}),
+            "dgrad_ffn_down_dgelu_tiled": (41984, 3072, 768, {"dgrad": True, "dgelu": True, "tiled": True}),
             "dgrad_qkv_accum": (41984, 768, 2304, {"dgrad": True, "add": True}),
             "wgrad_ffn_up": (3072, 768, 41984, {"wgrad": True}),
             "wgrad_attn_out": (768, 768, 41984, {"wgrad": True}),
@@ -143,7 +145,7 @@ def run_case(name):
                 args = dict(A=A.data_ptr(), lda=K, B=B.data_ptr(), ldb=N, b_mn_major=1, M=M, N=N, K=K, D=D.data_ptr(), ldd=N)
                 if kw.get("dgelu"):
                     U = rnd(M, N)
-                    args.update(epilogue=_lib.VB_EPI_DGELU, aux_in=U.data_ptr(), ld_aux=N)
+                    args.update(epilogue=_lib.VB_EPI_DGELU, aux_in=U.data_ptr(), ld_aux=N, gp_tiled=1 if kw.get("tiled") else 0)
                 if kw.get("add"):
                     R = rnd(M, N)
                     args.update(addend=R.data_ptr(), ld_add=N)
@@ -162,7 +164,8 @@ def run_case(name):
                 if kw.get("gelu"):
                     G = torch.zeros_like(D)
                     bias = torch.randn(N, device=dev)
-                    args.update(epilogue=kw.get("epi", _lib.VB_EPI_GELU), aux_out=G.data_ptr(), ld_aux=N, bias=bias.data_ptr())
+                    args.update(epilogue=kw.get("epi", _lib.VB_EPI_GELU), aux_out=G.data_ptr(), ld_aux=N, bias=bias.data_ptr(),
+                                gp_tiled=1 if kw.get("tiled") else 0)
             for _ in range(3):
                 call(**args)
             torch.cuda.synchronize()

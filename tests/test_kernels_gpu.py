@@ -62,6 +62,26 @@ def test_gemm_gelu_and_dgelu():
           epilogue=_lib.VB_EPI_DGELU, aux_in=U.data_ptr(), ld_aux=N)
     torch.cuda.synchronize()
     assert _rel(D, (A.float() @ B.float().t()) * U.float()) < BF16_TOL
+    # gelu'(u) in the library's tile-native order (what vb_layer_fwd / _bwd use for acts.u): same values, permuted; the DGELU
+    # epilogue of a GEMM with the same output shape consumes it
+    if L.vb_gemm_gp_tiled_ok(M, N):
+        Ut = torch.zeros_like(U); G2 = torch.zeros_like(U); D2 = torch.zeros_like(U)
+        _gemm(_lib, L, st, A=A.data_ptr(), lda=K, B=B.data_ptr(), ldb=K, M=M, N=N, K=K, D=Ut.data_ptr(), ldd=N,
+              bias=bias.data_ptr(), epilogue=_lib.VB_EPI_GELU, aux_out=G2.data_ptr(), ld_aux=N, gp_tiled=1)
+        torch.cuda.synchronize()
+        assert torch.equal(G2, G)
+        # documented layout: [M/256][N/256][2 ranks][2 column halves][4 row quarters][8 chunks][32 lanes][16]
+        t = Ut.view(M // 256, N // 256, 2, 2, 4, 8, 32, 16).permute(0, 2, 4, 6, 1, 3, 5, 7).reshape(M, N)
+        assert torch.equal(t, U)
+        Wd = (0.05 * torch.randn(K, N, device=dev)).bfloat16()   # dgrad form: D[M,N] = dY[M,K] W[K,N], B MN-major
+        Dref = torch.zeros_like(U)
+        _gemm(_lib, L, st, A=A.data_ptr(), lda=K, B=Wd.data_ptr(), ldb=N, b_mn_major=1, M=M, N=N, K=K, D=Dref.data_ptr(), ldd=N,
+              epilogue=_lib.VB_EPI_DGELU, aux_in=U.data_ptr(), ld_aux=N)
+        _gemm(_lib, L, st, A=A.data_ptr(), lda=K, B=Wd.data_ptr(), ldb=N, b_mn_major=1, M=M, N=N, K=K, D=D2.data_ptr(), ldd=N,
+              epilogue=_lib.VB_EPI_DGELU, aux_in=Ut.data_ptr(), ld_aux=N, gp_tiled=1)
+        torch.cuda.synchronize()
+        assert torch.equal(D2, Dref)
+        assert _rel(Dref, (A.float() @ Wd.float()) * U.float()) < BF16_TOL
 
 
 def test_gemm_dgrad_and_wgrad():

@@ -78,6 +78,7 @@ int layer_fwd(const vb_layer_desc* d, const void* x_in, void* x_out, const vb_la
     VB_TRY(ln_fwd(s->pre1, H, d->ln1_gamma, d->ln1_beta, s->x1, H, s->mean1, s->rstd1, M, H, kLnEps, st));
     a = fwd_args(s->x1, d->w_inter, s->u, M, I, H);
     a.bias = d->b_inter; a.epilogue = VB_EPI_GELU; a.aux_out = s->g; a.ld_aux = I;
+    a.gp_tiled = gemm_gp_tiled_ok(M, I) ? 1 : 0;   // acts.u is private to the library: tile-native whenever the shape allows
     VB_TRY(gemm(a, st));
     a = fwd_args(s->g, d->w_out, s->pre2, M, H, I);
     a.bias = d->b_out; a.addend = s->x1; a.ld_add = H;
@@ -103,6 +104,7 @@ int layer_bwd(const vb_layer_desc* d, const void* x_in, const vb_layer_acts* s, 
     VB_TRY(gemm(wgrad_args(dpm, s->g, g->dw_out, M, H, I), st));
     vb_gemm_args a = dgrad_args(dpm, d->w_out, w->d_big, M, H, I);  // d_g, then * gelu'(u) -> d_u
     a.epilogue = VB_EPI_DGELU; a.aux_in = s->u; a.ld_aux = I;
+    a.gp_tiled = gemm_gp_tiled_ok(M, I) ? 1 : 0;
     VB_TRY(gemm(a, st));
     // ---- BertIntermediate ----
     VB_TRY(colsum(w->d_big, I, g->db_inter, M, I, st));

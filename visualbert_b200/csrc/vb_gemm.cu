@@ -104,6 +104,8 @@ struct GemmParams {
     unsigned long long drop_seed;
     unsigned drop_stream;
 };
+// vb_gemm_args.gp_tiled is honoured by the CTA-pair kernel with the staged-store epilogue on whole tiles only
+bool gemm_gp_tiled_ok(int M, int N);
 
 // UMMA shared-memory matrix descriptor (sm_100: version = 1), SWIZZLE_128B.
 //  K-major  operand tile [rows][64]: 8-row groups are 1024 B apart (SBO); LBO unused.
@@ -166,7 +168,13 @@ __device__ __forceinline__ void store16_bf16(bf16* p, const float (&f)[16]) {
 // EPI selects the epilogue at COMPILE time for the CTA-pair kernel: the generic form (every option a run-time branch, all 8 chunks
 // unrolled) compiled to ~6 000 instructions (95 KB) per kernel — three times the SM's 32 KB L1.5 instruction cache, with
 // `no_instruction` stalls of 0.5-2.4 warps per issue cycle on the epilogue-bound launches. A specialised kernel carries only its path.
-enum { EPI_GENERIC = 0, EPI_BIAS = 1, EPI_RESID = 2, EPI_DROP_RESID = 3, EPI_GELU_FWD = 4, EPI_DGELU_BWD = 5 };
+// _T: gelu'(u) is kept in the TILE-NATIVE layout (vb_gemm_args.gp_tiled): the only reader of that tensor is the epilogue of the
+// backward GEMM with the same tiling, where the same thread holds the same 16 columns — so it is written and read as whole
+// 1 KB warp blocks (lane l: 32 bytes at block + 32 l) instead of 32-byte pieces of 32 different rows.
+enum { EPI_GENERIC = 0, EPI_BIAS = 1, EPI_RESID = 2, EPI_DROP_RESID = 3, EPI_GELU_FWD = 4, EPI_DGELU_BWD = 5, EPI_GELU_FWD_T = 6,
+       EPI_DGELU_BWD_T = 7 };
+__host__ __device__ constexpr bool epi_is_gelu(int e) { return e == EPI_GELU_FWD || e == EPI_GELU_FWD_T; }
+__host__ __device__ constexpr bool epi_is_dgelu(int e) { return e == EPI_DGELU_BWD || e == EPI_DGELU_BWD_T; }
 
 // TO_REGS: nothing is stored; the 16 bf16 results are returned packed in o0 (what goes to D) and, for the GELU epilogue,
 // o1 (what goes to aux_out) — the caller stages them in shared memory for a TMA store.
@@ -205,7 +213,7 @@ __device__ __forceinline__ void epilogue16(const GemmParams& p, int row, int col
             }
         }
         bf16* d = reinterpret_cast<bf16*>(p.D) + static_cast<long long>(row) * p.ldd + col;
-        if (EPI == EPI_GELU_FWD || (kGeneric && p.epilogue == VB_EPI_GELU)) {
+        if (epi_is_gelu(EPI) || (kGeneric && p.epilogue == VB_EPI_GELU)) {
             // aux_out <- gelu(u) (operand of the next GEMM), D <- gelu'(u) (all the backward needs of u)
             float gp[16];
 #pragma unroll
@@ -220,7 +228,7 @@ __device__ __forceinline__ void epilogue16(const GemmParams& p, int row, int col
         } else if (kGeneric && p.epilogue == 3) {  // debug/tuning only: two stores, no GELU math
             store16_bf16(d, x);
             d = p.aux_out + static_cast<long long>(row) * p.ld_aux + col;
-        } else if (EPI == EPI_DGELU_BWD || (kGeneric && p.epilogue == VB_EPI_DGELU)) {
+        } else if (epi_is_dgelu(EPI) || (kGeneric && p.epilogue == VB_EPI_DGELU)) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float2 t = unpack_bf16x2(ex[i]);
@@ -551,7 +559,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
     // Epilogues that read a second operand (residual / gelu') hold the whole tile row of it in registers (see below): the
     // four control warps hand registers to the eight epilogue warps (128 * 72 + 256 * 216 = 384 * 168).
-    constexpr bool kDeepEx = VB_GEMM_DEEP_EX && !OUT_F32 && (EPI == EPI_RESID || EPI == EPI_DROP_RESID || EPI == EPI_DGELU_BWD);
+    constexpr bool kDeepEx = VB_GEMM_DEEP_EX && !OUT_F32 && (EPI == EPI_RESID || EPI == EPI_DROP_RESID || epi_is_dgelu(EPI));
     if (warp == 0) {
         if constexpr (kDeepEx) reg_dec<72>();
         {
@@ -683,6 +691,12 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 else if (EPI == EPI_DGELU_BWD || (EPI == EPI_GENERIC && p.epilogue == VB_EPI_DGELU)) exp_ = p.aux_in + static_cast<long long>(row) * p.ld_aux;
                 if (row >= p.M) exp_ = nullptr;
             }
+            // chunk k of the operand: exb + k * ex_step. Row-major: 16 columns further in this thread's row. Tile-native gelu'(u)
+            // (M, N multiples of 256): the next 1 KB warp block of this warp's 8 KB region, lane l at + 32 l bytes.
+            constexpr long long ex_step = EPI == EPI_DGELU_BWD_T ? 512 : 16;
+            const long long gp_tile_off = ((((static_cast<long long>(tc.m_blk) * n_blocks + tc.n_blk) * 2 + rank) * kEpiWarps + ew) * NCH) * 512 + lane * 16;
+            const bf16* exb = exp_ != nullptr ? exp_ + col0 : nullptr;
+            if constexpr (EPI == EPI_DGELU_BWD_T) { exp_ = p.aux_in; exb = p.aux_in + gp_tile_off; }
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + half * (BLOCK_N / 2);
             uint32_t v[2][16];
             if constexpr (kDeepEx) {
@@ -694,10 +708,10 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 uint32_t exA[kExAhead][8], exB[kExAhead][8];
 #pragma unroll
                 for (int k = 0; k < kExAhead; ++k)
-                    if (exp_ != nullptr && col0 + k * 16 < p.N) ldg_v8(exp_ + col0 + k * 16, exA[k]);
+                    if (exp_ != nullptr && col0 + k * 16 < p.N) ldg_v8(exb + k * ex_step, exA[k]);
 #pragma unroll
                 for (int k = 0; k < kExAhead; ++k)
-                    if (exp_ != nullptr && col0 + (k + kExAhead) * 16 < p.N) ldg_v8(exp_ + col0 + (k + kExAhead) * 16, exB[k]);
+                    if (exp_ != nullptr && col0 + (k + kExAhead) * 16 < p.N) ldg_v8(exb + (k + kExAhead) * ex_step, exB[k]);
                 mbar_wait(tfull_bar(acc), acc_phase);
                 tcgen05_fence_after();
                 tmem_ld_32x32b_x16(taddr0, v[0]);
@@ -734,13 +748,13 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 uint32_t ex[kExAhead][8];
 #pragma unroll
                 for (int k = 0; k < kExAhead; ++k)
-                    if (exp_ != nullptr && col0 + k * 16 < p.N) ldg_v8(exp_ + col0 + k * 16, ex[k]);
+                    if (exp_ != nullptr && col0 + k * 16 < p.N) ldg_v8(exb + k * ex_step, ex[k]);
                 mbar_wait(tfull_bar(acc), acc_phase);
                 tcgen05_fence_after();
                 tmem_ld_32x32b_x16(taddr0, v[0]);
                 // chunks in groups: inside a group every buffer index is static; the group loop is NOT unrolled (code size)
                 // (epilogues without a prefetched operand only need the 2-deep TMEM double buffer: groups of 2 halve their code again)
-                constexpr int kGroup = (!kTmaSt && (EPI == EPI_GELU_FWD || EPI == EPI_BIAS)) ? 2 : kExAhead;  // staged stores: one slab = 4 chunks
+                constexpr int kGroup = (!kTmaSt && (epi_is_gelu(EPI) || EPI == EPI_BIAS)) ? 2 : kExAhead;  // staged stores: one slab = 4 chunks
                 static_assert(NCH % kGroup == 0, "chunk groups");
                 uint32_t gk[kTmaSt && EPI == EPI_GELU_FWD ? kGroup : 1][8];  // gelu(u) of the slab, stored after gelu'(u)
 #pragma unroll 1
@@ -755,7 +769,15 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                             float x[16];
 #pragma unroll
                             for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[kk & 1][i]);
-                            if constexpr (kTmaSt) {
+                            if constexpr (EPI == EPI_GELU_FWD_T) {
+                                // gelu'(u): one coalesced 1 KB warp store into the tile-native buffer; gelu(u): staged for the TMA store
+                                static_assert(kTmaSt, "the tile-native GELU epilogue stages gelu(u)");
+                                uint32_t o0[8], o1[8];
+                                epilogue16<OUT_F32, EPI, true>(p, row, col, has_bias ? sb + half * (BLOCK_N / 2) + k * 16 : nullptr, ex[kk], x, o0, o1);
+                                stg_v8(reinterpret_cast<bf16*>(p.D) + gp_tile_off + k * 512, o0);
+                                if (kk == 0) slab_free();
+                                stage16(kk, o1);
+                            } else if constexpr (kTmaSt) {
                                 uint32_t o0[8];
                                 epilogue16<OUT_F32, EPI, true>(p, row, col, has_bias ? sb + half * (BLOCK_N / 2) + k * 16 : nullptr, ex[kk], x, o0,
                                                                gk[EPI == EPI_GELU_FWD ? kk : 0]);
@@ -767,9 +789,11 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                         }
                         // buffer kk is free again: refill it with the operand of chunk k + kExAhead
                         if (k + kExAhead < NCH && exp_ != nullptr && col0 + (k + kExAhead) * 16 < p.N)
-                            ldg_v8(exp_ + col0 + (k + kExAhead) * 16, ex[kk]);
+                            ldg_v8(exb + (k + kExAhead) * ex_step, ex[kk]);
                     }
-                    if constexpr (kTmaSt) {
+                    if constexpr (EPI == EPI_GELU_FWD_T) {
+                        flush(&tmAux, col0 + k0 * 16);
+                    } else if constexpr (kTmaSt) {
                         flush(&tmD, col0 + k0 * 16);
                         if constexpr (EPI == EPI_GELU_FWD) {
                             slab_free();
@@ -997,6 +1021,10 @@ static bool use_2cta() {
     if (v < 0) { const char* e = getenv("VB_GEMM_2CTA"); v = (e != nullptr && atoi(e) == 0) ? 0 : 1; }
     return v == 1;
 }
+bool gemm_gp_tiled_ok(int M, int N) {
+    static const int off = [] { const char* e = getenv("VB_GEMM_GP_TILED"); return (e != nullptr && atoi(e) == 0) ? 1 : 0; }();
+    return !off && use_2cta() && M >= 256 && M % 256 == 0 && N % 256 == 0;
+}
 
 int gemm(const vb_gemm_args& a, cudaStream_t st) {
     VB_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "vb_gemm: empty problem M=%d N=%d K=%d", a.M, a.N, a.K);
@@ -1014,6 +1042,8 @@ int gemm(const vb_gemm_args& a, cudaStream_t st) {
     VB_REQUIRE(!a.d_fp32 || (a.epilogue == VB_EPI_NONE && !a.addend && a.dropout_p == 0.0f),
                "vb_gemm: fp32-accumulate output supports bias only");
     VB_REQUIRE(a.dropout_p >= 0.0f && a.dropout_p < 1.0f, "vb_gemm: dropout_p out of range");
+    VB_REQUIRE(!a.gp_tiled || (gemm_gp_tiled_ok(a.M, a.N) && !a.d_fp32 && !a.a_mn_major && (a.epilogue == VB_EPI_GELU || a.epilogue == VB_EPI_DGELU)),
+               "vb_gemm: gp_tiled needs a GELU / DGELU epilogue and vb_gemm_gp_tiled_ok(M, N)");
 
     GemmParams p;
     memset(&p, 0, sizeof(p));
@@ -1056,23 +1086,25 @@ int gemm(const vb_gemm_args& a, cudaStream_t st) {
             // specialised epilogues for the shapes of the layer (forward and input-gradient GEMMs); anything else: generic
             const bool drop = a.dropout_p > 0.0f, add = a.addend != nullptr;
             int epi = EPI_GENERIC;
-            if (a.epilogue == VB_EPI_GELU && !drop && !add) epi = EPI_GELU_FWD;
-            else if (a.epilogue == VB_EPI_DGELU && !drop && !add) epi = EPI_DGELU_BWD;
+            if (a.epilogue == VB_EPI_GELU && !drop && !add) epi = a.gp_tiled ? EPI_GELU_FWD_T : EPI_GELU_FWD;
+            else if (a.epilogue == VB_EPI_DGELU && !drop && !add) epi = a.gp_tiled ? EPI_DGELU_BWD_T : EPI_DGELU_BWD;
             else if (a.epilogue == VB_EPI_NONE) epi = add ? (drop ? EPI_DROP_RESID : EPI_RESID) : (drop ? EPI_GENERIC : EPI_BIAS);
+            VB_REQUIRE(!a.gp_tiled || epi == EPI_GELU_FWD_T || epi == EPI_DGELU_BWD_T,
+                       "vb_gemm: gp_tiled needs a plain GELU / DGELU epilogue (no dropout, no addend)");
             // Staged TMA stores where the epilogue, not the main loop, bounds the tile (measured r02, same box, us per
             // launch with / without: FFN-up + GELU 200 / 214, attention-output 59 / 66, but K = 3072 or bias-only epilogues
             // 3-4 us SLOWER — the slabs cost a pipeline stage). VB_GEMM_TMA_STORE=0 / 1 forces never / wherever possible.
             static const int tma_mode = [] { const char* e = getenv("VB_GEMM_TMA_STORE"); return e ? atoi(e) : 2; }();
             bool tma_st = false;
-            if (tma_mode == 1) tma_st = epi != EPI_GENERIC;
+            if (tma_mode == 1 || epi == EPI_GELU_FWD_T) tma_st = epi != EPI_GENERIC;
             else if (tma_mode != 0)
-                tma_st = epi == EPI_GELU_FWD || epi == EPI_DGELU_BWD || ((epi == EPI_RESID || epi == EPI_DROP_RESID) && a.K <= 1536);
+                tma_st = epi_is_gelu(epi) || epi_is_dgelu(epi) || ((epi == EPI_RESID || epi == EPI_DROP_RESID) && a.K <= 1536);
             // output tensor maps for the staged TMA stores: 64-column x 32-row boxes (one epilogue warp's slab)
             CUtensorMap td = ta, tx = ta;
             if (tma_st) {
                 rc = make_tmap_bf16(&td, a.D, a.N, a.M, a.ldd, 32);
                 if (rc) return rc;
-                if (epi == EPI_GELU_FWD) {
+                if (epi_is_gelu(epi)) {
                     rc = make_tmap_bf16(&tx, a.aux_out, a.N, a.M, a.ld_aux, 32);
                     if (rc) return rc;
                 }
@@ -1107,6 +1139,7 @@ int gemm(const vb_gemm_args& a, cudaStream_t st) {
                     case EPI_RESID: return (tma_st ? launch2<false, false, false, EPI_RESID, true>(ta, tb, td, tx, p, st) : launch2<false, false, false, EPI_RESID, false>(ta, tb, td, tx, p, st));
                     case EPI_DROP_RESID: return (tma_st ? launch2<false, false, false, EPI_DROP_RESID, true>(ta, tb, td, tx, p, st) : launch2<false, false, false, EPI_DROP_RESID, false>(ta, tb, td, tx, p, st));
                     case EPI_GELU_FWD: return (tma_st ? launch2<false, false, false, EPI_GELU_FWD, true>(ta, tb, td, tx, p, st) : launch2<false, false, false, EPI_GELU_FWD, false>(ta, tb, td, tx, p, st));
+                    case EPI_GELU_FWD_T: return launch2<false, false, false, EPI_GELU_FWD_T, true>(ta, tb, td, tx, p, st);
                     default: return launch2<false, false, false>(ta, tb, ta, ta, p, st);
                 }
             }
@@ -1115,6 +1148,7 @@ int gemm(const vb_gemm_args& a, cudaStream_t st) {
                     case EPI_BIAS: return (tma_st ? launch2<false, true, false, EPI_BIAS, true>(ta, tb, td, tx, p, st) : launch2<false, true, false, EPI_BIAS, false>(ta, tb, td, tx, p, st));
                     case EPI_RESID: return (tma_st ? launch2<false, true, false, EPI_RESID, true>(ta, tb, td, tx, p, st) : launch2<false, true, false, EPI_RESID, false>(ta, tb, td, tx, p, st));
                     case EPI_DGELU_BWD: return (tma_st ? launch2<false, true, false, EPI_DGELU_BWD, true>(ta, tb, td, tx, p, st) : launch2<false, true, false, EPI_DGELU_BWD, false>(ta, tb, td, tx, p, st));
+                    case EPI_DGELU_BWD_T: return (tma_st ? launch2<false, true, false, EPI_DGELU_BWD_T, true>(ta, tb, td, tx, p, st) : launch2<false, true, false, EPI_DGELU_BWD_T, false>(ta, tb, td, tx, p, st));
                     default: return launch2<false, true, false>(ta, tb, ta, ta, p, st);
                 }
             }
@@ -1173,6 +1207,7 @@ int vb_profile_read(double* ms, double* work, int64_t* launches) {
     vb::g_prof.clear();
     return 0;
 }
+int vb_gemm_gp_tiled_ok(int32_t M, int32_t N) { return vb::gemm_gp_tiled_ok(M, N) ? 1 : 0; }
 int vb_gemm(const vb_gemm_args* args, void* stream) {
     if (!args) { vb::set_error("vb_gemm: null args"); return 2; }
     return vb::gemm(*args, static_cast<cudaStream_t>(stream));

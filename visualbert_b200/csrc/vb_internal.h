@@ -6,6 +6,7 @@
 namespace vb {
 
 int gemm(const vb_gemm_args& a, cudaStream_t st);
+bool gemm_gp_tiled_ok(int M, int N);
 int ln_fwd(const void* x, long long ldx, const float* gamma, const float* beta, void* y, long long ldy, float* mean,
            float* rstd, int rows, int H, float eps, cudaStream_t st);
 int ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
