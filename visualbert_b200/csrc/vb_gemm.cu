@@ -963,10 +963,11 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
 
 // Quad variant (two CTA pairs per cluster sharing the B tile by TMA multicast). Returns -1 when clusters of four cannot be
 // placed on this device (the caller then uses the pair kernel).
-template <bool B_MN, int EPI>
+template <bool B_MN, int EPI, bool TMA_ST = false>
 static int launch4(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tx, const GemmParams& p,
                    cudaStream_t st) {
-    auto kern = gemm_tcgen05_2cta_kernel<false, B_MN, false, EPI, 4>;
+    auto kern = gemm_tcgen05_2cta_kernel<false, B_MN, false, EPI, 4, TMA_ST>;
+    using Cfg2 = Cfg2T<TMA_ST>;
     static int configured[kMaxDevices] = {0};
     static int resident[kMaxDevices] = {0};  // clusters of four that fit on the device at once (0 = not asked yet)
     VB_CHECK_CUDA(ensure_dyn_smem(kern, Cfg2::SMEM_BYTES, configured));
@@ -992,8 +993,7 @@ static int launch4(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
     if (clusters > tiles) clusters = tiles;
     {
         ProfScope ps(st, B_MN ? PROF_GEMM_DGRAD : PROF_GEMM_FWD, 2.0 * p.M * p.N * p.K, 1);
-        (void)td; (void)tx;
-        VB_CHECK_CUDA(launch_pdl_cluster(kern, dim3(4 * clusters), dim3(kThreads), Cfg2::SMEM_BYTES, st, 4, ta, tb, ta, ta, p));
+        VB_CHECK_CUDA(launch_pdl_cluster(kern, dim3(4 * clusters), dim3(kThreads), Cfg2::SMEM_BYTES, st, 4, ta, tb, td, tx, p));
     }
     VB_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -1001,11 +1001,12 @@ static int launch4(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
 // VB_GEMM_QUAD=1 opts in to the quad kernels. Off by default: measured on B200 (r02, scripts/gpu_check_gemm.py perf) only
 // 33 clusters of four are co-resident (132 of 148 SMs) and the saved L2 traffic does not make up for the idle SMs — the
 // layer's GEMMs are 5-9 % slower than on the pair kernel (DESIGN.md "negative results").
-static bool use_quad() {
+static int quad_mode() {   // 0: never, 1: every specialised epilogue, 2: only the tile-native GELU / DGELU launches
     static int v = -1;
-    if (v < 0) { const char* e = getenv("VB_GEMM_QUAD"); v = (e != nullptr && atoi(e) == 1) ? 1 : 0; }
-    return v == 1;
+    if (v < 0) { const char* e = getenv("VB_GEMM_QUAD"); v = e != nullptr ? atoi(e) : 0; }
+    return v;
 }
+static bool use_quad() { return quad_mode() == 1; }
 
 bool pdl_enabled() {
     static const bool on = [] {
@@ -1110,7 +1111,19 @@ int gemm(const vb_gemm_args& a, cudaStream_t st) {
                 }
             }
             // quad clusters for the tall activation GEMMs of the layer (at least two 256-row blocks to pair up)
-            if (use_quad() && epi != EPI_GENERIC && !a.a_mn_major && a.M > 256) {
+            if (quad_mode() == 2 && a.M > 256) {
+                int q = -1;
+                if (epi == EPI_GELU_FWD_T) {
+                    CUtensorMap tq;
+                    rc = make_tmap_bf16(&tq, a.B, a.K, a.N, a.ldb, 64);
+                    if (rc) return rc;
+                    q = launch4<false, EPI_GELU_FWD_T, true>(ta, tq, td, tx, p, st);
+                } else if (epi == EPI_DGELU_BWD_T && a.b_mn_major) {
+                    q = launch4<true, EPI_DGELU_BWD_T, true>(ta, tb, td, tx, p, st);
+                }
+                if (q >= 0) return q;
+            }
+            if (use_quad() && epi != EPI_GENERIC && epi != EPI_GELU_FWD_T && epi != EPI_DGELU_BWD_T && !a.a_mn_major && a.M > 256) {
                 CUtensorMap tq;  // K-major B is fetched in 64-row boxes (half of a CTA's part), MN-major B already is
                 int q = 1;
                 if (!a.b_mn_major) {
