@@ -131,6 +131,7 @@ def run_case(name):
             "dgrad_qkv_accum": (41984, 768, 2304, {"dgrad": True, "add": True}),
             "wgrad_ffn_up": (3072, 768, 41984, {"wgrad": True}),
             "wgrad_attn_out": (768, 768, 41984, {"wgrad": True}),
+            "wgrad_ffn_down": (768, 3072, 41984, {"wgrad": True}),
         }.items():
             if kw.get("wgrad"):
                 A = rnd(K, M); B = rnd(K, N)

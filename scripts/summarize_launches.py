@@ -12,7 +12,7 @@ seg = launches[marks[-2]:marks[-1]]
 
 def family(n):
     n = n.replace("void ", "").replace("vb::", "").replace("<unnamed>::", "")
-    m = re.match(r"(gemm_tcgen05(?:_2cta)?_kernel)<(\d), (\d), (\d+)(?:, (\d))?>", n)
+    m = re.match(r"(gemm_tcgen05(?:_2cta)?_kernel)<(\d), (\d), (\d+)(?:, [^>]*)?>", n)
     if m:
         a, b = m.group(2), m.group(3)
         kind = {"00": "fwd (K-major A, K-major B)", "01": "dgrad (B MN-major)", "11": "wgrad (A,B MN-major, fp32 red.add)"}.get(a + b, a + b)

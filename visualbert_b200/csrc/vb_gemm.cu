@@ -103,6 +103,7 @@ struct GemmParams {
     unsigned drop_thresh16;  // n = round(p * 256): 8-bit keep threshold (see dropout_quantise)
     unsigned long long drop_seed;
     unsigned drop_stream;
+    int m_fast;              // tile order of the CTA-pair kernel: m-blocks run faster than n-blocks (see decode_tile)
 };
 // vb_gemm_args.gp_tiled is honoured by the CTA-pair kernel with the staged-store epilogue on whole tiles only
 bool gemm_gp_tiled_ok(int M, int N);
@@ -131,12 +132,21 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
 struct TileCoord {
     int m_blk, n_blk, kb_begin, kb_end;
 };
-__device__ __forceinline__ TileCoord decode_tile(int t, int n_blocks, int splits, int k_blocks) {
+// Tile order: the split index runs fastest, then the dimension with FEWER blocks (m_fast: there are fewer m-blocks), so that the
+// tiles in flight at any time share the slabs of the operand that spans the dimension with MORE blocks — the big one, which
+// must not be fetched from DRAM once per block of the other dimension (FFN-down weight gradient: M = 768, N = 3072, B = gelu(u)
+// is 258 MB, twice the L2: n-fastest order read it 2.4 times, profiles/r02b_layer_kernels_table.md).
+__device__ __forceinline__ TileCoord decode_tile(int t, int n_blocks, int splits, int k_blocks, int m_blocks = 0, bool m_fast = false) {
     TileCoord c;
     const int split = t % splits;
     const int mn = t / splits;
-    c.n_blk = mn % n_blocks;
-    c.m_blk = mn / n_blocks;
+    if (m_fast) {
+        c.m_blk = mn % m_blocks;
+        c.n_blk = mn / m_blocks;
+    } else {
+        c.n_blk = mn % n_blocks;
+        c.m_blk = mn / n_blocks;
+    }
     c.kb_begin = static_cast<int>(static_cast<long long>(split) * k_blocks / splits);
     c.kb_end = static_cast<int>(static_cast<long long>(split + 1) * k_blocks / splits);
     return c;
@@ -551,7 +561,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int num_tiles = kQuad ? ((m_blocks + 1) / 2) * n_blocks : m_blocks * n_blocks * p.splits;
     const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
     auto tile_of = [&](int t) {
-        TileCoord c = decode_tile(t, n_blocks, kQuad ? 1 : p.splits, k_blocks);
+        TileCoord c = decode_tile(t, n_blocks, kQuad ? 1 : p.splits, k_blocks, m_blocks, !kQuad && p.m_fast != 0);
         if constexpr (kQuad) c.m_blk = c.m_blk * 2 + static_cast<int>(pair);
         return c;
     };
@@ -1060,6 +1070,10 @@ int gemm(const vb_gemm_args& a, cudaStream_t st) {
     p.aux_in = static_cast<const bf16*>(a.aux_in);
     p.aux_out = static_cast<bf16*>(a.aux_out);
     p.ld_aux = a.ld_aux;
+    {
+        static const int order_off = [] { const char* e = getenv("VB_GEMM_TILE_ORDER"); return (e != nullptr && atoi(e) == 0) ? 1 : 0; }();
+        p.m_fast = (!order_off && (a.M + 255) / 256 < (a.N + 255) / 256) ? 1 : 0;
+    }
     if (a.dropout_p > 0.0f) {
         const DropQ q = dropout_quantise(a.dropout_p);
         p.drop_scale = q.scale;
