@@ -385,10 +385,12 @@ def run_ours(args):
     step_tf = (value / world) * F / 1e12
     kern_ms = {k: round(v["ms"] / args.steps, 3) for k, v in prof.items()}
     traffic, traffic_src = None, None
-    tj = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_traffic.json")
-    if os.path.exists(tj) and args.config == "cfg2" and B == 256:  # the ncu capture is of this workload only
-        tr = json.load(open(tj))
-        traffic, traffic_src = tr["gemm_dram_bytes_per_launch_avg"], f"profiles/r02_traffic.json ({tr['source']})"
+    for tname in ("r02b_traffic.json", "r02_traffic.json"):   # newest committed capture first
+        tj = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", tname)
+        if os.path.exists(tj) and args.config == "cfg2" and B == 256:  # the ncu capture is of this workload only
+            tr = json.load(open(tj))
+            traffic, traffic_src = tr["gemm_dram_bytes_per_launch_avg"], f"profiles/{tname} ({tr['source']})"
+            break
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
