@@ -110,44 +110,81 @@ embed_fwd_kernel(const EmbedParams p) {
     }
 }
 
-// smem: [n_types][H] text types, [n_types][H] visual types, [H] visual position row 0
+// Adjoint of the gather / concat: word rows are scattered with vector reductions; the position, token-type and visual
+// position / type gradients — a few rows that EVERY example adds into — are first summed in registers over a chunk of
+// examples at a fixed sequence position (a warp task = (position s, 32 examples)), so each table row receives one vector
+// reduction per task instead of one scalar atomic per element (round 1: 0.28 ms, almost all of it atomic contention).
+// smem: [n_types][H] text types, [n_types][H] visual types, [H] visual position row 0 (block accumulators, flushed once)
+template <int NC>
 __global__ void __launch_bounds__(kEmbWarps * 32)
-embed_bwd_kernel(const EmbedBwdParams p) {
+embed_bwd_kernel(const EmbedBwdParams p, int cb, int nb) {
     extern __shared__ float acc[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int H = p.H, chunks = H >> 3, S = p.T + p.V, nt = p.n_types;
     const int nacc = (2 * nt + 1) * H;
     for (int i = threadIdx.x; i < nacc; i += blockDim.x) acc[i] = 0.f;
     __syncthreads();
-    const long long rows = static_cast<long long>(p.B) * S;
-    for (long long row = static_cast<long long>(blockIdx.x) * kEmbWarps + warp; row < rows;
-         row += static_cast<long long>(gridDim.x) * kEmbWarps) {
-        const int b = static_cast<int>(row / S), s = static_cast<int>(row % S);
-        float *g0, *a0, *a1 = nullptr;
-        bf16* dv = nullptr;
-        if (s < p.T) {
-            g0 = p.dword + static_cast<long long>(clampi(p.ids[static_cast<long long>(b) * p.T + s], p.vocab)) * H;
-            a0 = acc + clampi(p.tt[static_cast<long long>(b) * p.T + s], nt) * H;
-        } else {
-            const int v = s - p.T;
-            g0 = nullptr;
-            dv = p.dvis + (static_cast<long long>(b) * p.V + v) * H;
-            a0 = acc + (nt + clampi(p.vt[static_cast<long long>(b) * p.V + v], nt)) * H;
-            a1 = acc + 2 * nt * H;
-        }
-        float* gp = (s < p.T) ? p.dpos + static_cast<long long>(s < p.max_pos ? s : p.max_pos - 1) * H : nullptr;
-        for (int ch = lane; ch < chunks; ch += 32) {
-            const uint4 u = ldg_v4(p.de + row * H + ch * 8);
-            if (dv != nullptr) stg_v4(dv + ch * 8, u);
-            const float2 x0 = unpack_bf16x2(u.x), x1 = unpack_bf16x2(u.y), x2 = unpack_bf16x2(u.z), x3 = unpack_bf16x2(u.w);
-            const float d[8] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y, x3.x, x3.y};
+    const int tasks = S * nb;
+    for (int task = blockIdx.x * kEmbWarps + warp; task < tasks; task += gridDim.x * kEmbWarps) {
+        const int s = task % S, bc = task / S;
+        const int b0 = bc * cb, b1 = min(p.B, b0 + cb);
+        const bool text = s < p.T;
+        float psum[NC][8], t0[NC][8], t1[NC][8];   // position row, token types 0 / 1 (other types: shared-memory atomics)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int col = ch * 8 + i;
-                if (g0 != nullptr) atomicAdd(g0 + col, d[i]);
-                if (gp != nullptr) atomicAdd(gp + col, d[i]);
-                atomicAdd(a0 + col, d[i]);
-                if (a1 != nullptr) atomicAdd(a1 + col, d[i]);
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) psum[c][i] = t0[c][i] = t1[c][i] = 0.f;
+        for (int b = b0; b < b1; ++b) {
+            const long long row = static_cast<long long>(b) * S + s;
+            float* g0 = nullptr;
+            bf16* dv = nullptr;
+            int ty;
+            if (text) {
+                g0 = p.dword + static_cast<long long>(clampi(p.ids[static_cast<long long>(b) * p.T + s], p.vocab)) * H;
+                ty = clampi(p.tt[static_cast<long long>(b) * p.T + s], nt);
+            } else {
+                dv = p.dvis + (static_cast<long long>(b) * p.V + (s - p.T)) * H;
+                ty = clampi(p.vt[static_cast<long long>(b) * p.V + (s - p.T)], nt);
+            }
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const int ch = lane + c * 32;
+                if (ch < chunks) {
+                    const uint4 u = ldg_v4(p.de + row * H + ch * 8);
+                    if (dv != nullptr) stg_v4(dv + ch * 8, u);
+                    const float2 x0 = unpack_bf16x2(u.x), x1 = unpack_bf16x2(u.y), x2 = unpack_bf16x2(u.z), x3 = unpack_bf16x2(u.w);
+                    const float d[8] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y, x3.x, x3.y};
+                    if (g0 != nullptr) {
+                        red_add_v4_f32(g0 + ch * 8, d[0], d[1], d[2], d[3]);
+                        red_add_v4_f32(g0 + ch * 8 + 4, d[4], d[5], d[6], d[7]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        psum[c][i] += d[i];
+                        if (ty == 0) t0[c][i] += d[i];
+                        else if (ty == 1) t1[c][i] += d[i];
+                        else atomicAdd(acc + ((text ? 0 : nt) + ty) * H + ch * 8 + i, d[i]);
+                    }
+                }
+            }
+        }
+        // flush the task: position row (text: global table row s; visual: the block's accumulator of visual position 0), types
+        float* prow = text ? p.dpos + static_cast<long long>(s < p.max_pos ? s : p.max_pos - 1) * H : nullptr;
+        float* a0 = acc + (text ? 0 : nt) * H;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const int ch = lane + c * 32;
+            if (ch < chunks) {
+                if (prow != nullptr) {
+                    red_add_v4_f32(prow + ch * 8, psum[c][0], psum[c][1], psum[c][2], psum[c][3]);
+                    red_add_v4_f32(prow + ch * 8 + 4, psum[c][4], psum[c][5], psum[c][6], psum[c][7]);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (prow == nullptr) atomicAdd(acc + 2 * nt * H + ch * 8 + i, psum[c][i]);
+                    atomicAdd(a0 + ch * 8 + i, t0[c][i]);
+                    if (nt > 1) atomicAdd(a0 + H + ch * 8 + i, t1[c][i]);
+                }
             }
         }
     }
@@ -255,16 +292,26 @@ int embed_fwd(const EmbedParams& p, cudaStream_t st) {
 }
 
 int embed_bwd(const EmbedBwdParams& p, cudaStream_t st) {
-    VB_REQUIRE(p.H % 8 == 0, "embed backward: H must be a multiple of 8");
+    VB_REQUIRE(p.H % 8 == 0 && p.H <= 1024, "embed backward: H=%d must be a multiple of 8 and <= 1024", p.H);
+    VB_REQUIRE((reinterpret_cast<uintptr_t>(p.dword) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.dpos) & 15) == 0,
+               "embed backward: gradient tables must be 16-byte aligned");
     const long long rows = static_cast<long long>(p.B) * (p.T + p.V);
+    const int cb = p.B < 32 ? p.B : 32, nb = (p.B + cb - 1) / cb;   // a warp task: one sequence position, up to 32 examples
+    const long long tasks = static_cast<long long>(p.T + p.V) * nb;
     int grid = num_sms() * 2;
-    const long long need = (rows + kEmbWarps - 1) / kEmbWarps;
+    const long long need = (tasks + kEmbWarps - 1) / kEmbWarps;
     if (grid > need) grid = static_cast<int>(need);
     const size_t smem = static_cast<size_t>(2 * p.n_types + 1) * p.H * sizeof(float);
     VB_REQUIRE(smem <= 48 * 1024, "embed backward: type_vocab_size * hidden too large for shared memory");
+    const int nc = (p.H / 8 + 31) / 32;
     {
         ProfScope ps(st, PROF_EMBED, 6.0 * rows * p.H, 1);
-        embed_bwd_kernel<<<grid, kEmbWarps * 32, smem, st>>>(p);
+        switch (nc) {
+            case 1: embed_bwd_kernel<1><<<grid, kEmbWarps * 32, smem, st>>>(p, cb, nb); break;
+            case 2: embed_bwd_kernel<2><<<grid, kEmbWarps * 32, smem, st>>>(p, cb, nb); break;
+            case 3: embed_bwd_kernel<3><<<grid, kEmbWarps * 32, smem, st>>>(p, cb, nb); break;
+            default: embed_bwd_kernel<4><<<grid, kEmbWarps * 32, smem, st>>>(p, cb, nb); break;
+        }
     }
     VB_CHECK_CUDA(cudaGetLastError());
     return 0;
