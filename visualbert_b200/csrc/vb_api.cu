@@ -68,9 +68,23 @@ int layer_fwd(const vb_layer_desc* d, const void* x_in, void* x_out, const vb_la
     const int M = d->batch * d->seq, H = d->hidden, I = d->inter;
     vb_gemm_args a = fwd_args(x_in, d->w_qkv, s->qkv, M, 3 * H, H);
     a.bias = d->b_qkv;
+    // the attention-dropout bits depend on (seed, layer) only: they are drawn on a side stream UNDER the QKV GEMM (attn_mask_async)
+    static cudaEvent_t before_qkv[kMaxDevices] = {nullptr};
+    const int dev = current_device();
+    const bool want_mask = d->attn_dropout > 0.f && s->keep_mask != nullptr;
+    if (want_mask) {
+        if (before_qkv[dev] == nullptr) VB_CHECK_CUDA(cudaEventCreateWithFlags(&before_qkv[dev], cudaEventDisableTiming));
+        VB_CHECK_CUDA(cudaEventRecord(before_qkv[dev], st));
+    }
     VB_TRY(gemm(a, st));
+    int mask_ready = 0;
+    if (want_mask) {
+        mask_ready = attn_mask_async(s->keep_mask, d->batch, d->seq, d->heads, H, d->attn_dropout, d->seed,
+                                     drop_stream(d->layer_index, kSiteAttnProbs), before_qkv[dev], st);
+        if (mask_ready < 0) return 2;
+    }
     VB_TRY(attn_fwd(s->qkv, d->mask_bias, s->ctx, s->lse, s->keep_mask, d->batch, d->seq, d->heads, H, d->attn_dropout, d->seed,
-                    drop_stream(d->layer_index, kSiteAttnProbs), st));
+                    drop_stream(d->layer_index, kSiteAttnProbs), st, mask_ready == 1));
     a = fwd_args(s->ctx, d->w_attn_out, s->pre1, M, H, H);
     a.bias = d->b_attn_out; a.addend = x_in; a.ld_add = H;
     a.dropout_p = d->hidden_dropout; a.dropout_seed = d->seed; a.dropout_stream = drop_stream(d->layer_index, kSiteAttnOut);

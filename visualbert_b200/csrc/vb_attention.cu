@@ -469,8 +469,44 @@ long long attn_keep_bytes(int B, int S, int A) {
     return 2 * static_cast<long long>(B) * A * (nkb * kBlk) * nkb * 8;  // query-major words + their transpose (key-major)
 }
 
+// Draws the attention-dropout keep bits of a layer on the library's SIDE stream, so that the ALU-only mask kernel (no memory
+// traffic, 32 registers, no shared memory) shares the SMs with the QKV projection GEMM instead of running alone for 35 us:
+// call it right after enqueuing that GEMM with an event recorded on `main` BEFORE the GEMM (the bits depend on (seed, stream)
+// only). Returns 1 when the bits are on their way (`main` already waits for them: pass mask_ready = true to attn_fwd), 0 when
+// the caller's attn_fwd will draw them itself (no dropout, another attention implementation, not opted in), < 0 on error.
+// OPT-IN (VB_MASK_OVERLAP=1): measured r02 on one box, 2 x 2 bench runs: 28.59 / 28.57 ms without, 28.87 / 28.56 ms with — the GEMM
+// slows down by what the mask kernel saves (its epilogue warps share the schedulers), so the default stays the plain sequence.
+int attn_mask_async(void* keep, int B, int S, int A, int H, float dropout_p, unsigned long long seed, unsigned stream_id,
+                    cudaEvent_t before_gemm, cudaStream_t main) {
+    static const int off = [] { const char* e = getenv("VB_MASK_OVERLAP"); return (e != nullptr && atoi(e) == 1) ? 0 : 1; }();
+    if (off || dropout_p <= 0.f || keep == nullptr) return 0;
+    const char* e = getenv("VB_ATTN_FWD_IMPL");
+    if ((e != nullptr && e[0] != 't') || staged_only()) return 0;
+    AttnParams p;
+    if (fill_params(p, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, keep, B, S, A, H, dropout_p, seed, stream_id)) return -1;
+    p.qkv = reinterpret_cast<const bf16*>(keep);   // only the alignment of qkv is looked at below; the mask kernel never reads it
+    if (!attn_fwd_tc_supported(p)) return 0;
+    static cudaStream_t side[kMaxDevices] = {nullptr};
+    static cudaEvent_t done[kMaxDevices] = {nullptr};
+    const int dev = current_device();
+    if (side[dev] == nullptr) {
+        if (cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&done[dev], cudaEventDisableTiming) != cudaSuccess) {
+            set_error("attention mask: cannot create the side stream");
+            return -1;
+        }
+    }
+    if (cudaStreamWaitEvent(side[dev], before_gemm, 0) != cudaSuccess) { set_error("attention mask: stream wait failed"); return -1; }
+    if (attn_keep_mask(p, (S + kBlk - 1) / kBlk, side[dev])) return -1;
+    if (cudaEventRecord(done[dev], side[dev]) != cudaSuccess || cudaStreamWaitEvent(main, done[dev], 0) != cudaSuccess) {
+        set_error("attention mask: event record / wait failed");
+        return -1;
+    }
+    return 1;
+}
+
 int attn_fwd(const void* qkv, const float* mask_bias, void* ctx, float* lse, void* keep, int B, int S, int A, int H,
-             float dropout_p, unsigned long long seed, unsigned stream_id, cudaStream_t st) {
+             float dropout_p, unsigned long long seed, unsigned stream_id, cudaStream_t st, bool mask_ready) {
     AttnParams p;
     int rc = fill_params(p, qkv, mask_bias, ctx, lse, nullptr, nullptr, nullptr, keep, B, S, A, H, dropout_p, seed, stream_id);
     if (rc) return rc;
@@ -484,8 +520,10 @@ int attn_fwd(const void* qkv, const float* mask_bias, void* ctx, float* lse, voi
         impl = e == nullptr ? 0 : (e[0] == 't' ? 0 : (e[0] == 's' ? 2 : 1));
     }
     if (impl == 0 && !staged_only() && attn_fwd_tc_supported(p)) {
-        rc = attn_keep_mask(p, static_cast<int>(grid.x), st);
-        if (rc) return rc;
+        if (!mask_ready) {
+            rc = attn_keep_mask(p, static_cast<int>(grid.x), st);
+            if (rc) return rc;
+        }
         return attn_fwd_tc(p, st);
     }
     if (impl <= 1 && static_cast<int>(grid.x) <= kMaxSub && !staged_only()) return attn_fwd_head(p, static_cast<int>(grid.x), st);
@@ -559,7 +597,7 @@ int vb_attention_fwd(const void* qkv, const float* mask_bias, void* ctx, float* 
                      int32_t seq, int32_t heads, int32_t hidden, float dropout_p, uint64_t dropout_seed,
                      uint32_t dropout_stream, void* stream) {
     return vb::attn_fwd(qkv, mask_bias, ctx, lse, keep_mask, batch, seq, heads, hidden, dropout_p, dropout_seed,
-                        dropout_stream, static_cast<cudaStream_t>(stream));
+                        dropout_stream, static_cast<cudaStream_t>(stream), false);
 }
 int vb_attention_bwd(const void* qkv, const float* mask_bias, const void* ctx, const float* lse, const void* keep_mask,
                      const void* dctx, void* dqkv, float* drow, int32_t batch, int32_t seq, int32_t heads,

@@ -229,7 +229,9 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __rest
 }
 
 // out[N] += column sums of x[M, N] (bf16). block = 32 x 8: x -> 8-column chunk, y -> row phase; four rows per
-// iteration so every thread keeps 4 x 16 B loads in flight (the kernel is pure HBM streaming).
+// iteration so every thread keeps 4 x 16 B loads in flight (the kernel is pure HBM streaming). The rows are swept from the
+// LAST to the first: the tensor was just written by the previous kernel, whose tiles run in increasing row order, so its tail
+// is what the L2 still holds.
 __global__ void __launch_bounds__(256)
 colsum_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ out, int M, int N) {
     __shared__ float red[8][32][9];
@@ -243,7 +245,7 @@ colsum_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ out,
         for (; r + 3 * stride < M; r += 4 * stride) {
             uint4 u[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) u[j] = ldg_v4(x + static_cast<long long>(r + j * stride) * ld + ch * 8);
+            for (int j = 0; j < 4; ++j) u[j] = ldg_v4(x + static_cast<long long>(M - 1 - (r + j * stride)) * ld + ch * 8);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float2 x0 = unpack_bf16x2(u[j].x), x1 = unpack_bf16x2(u[j].y), x2 = unpack_bf16x2(u[j].z), x3 = unpack_bf16x2(u[j].w);
@@ -251,7 +253,7 @@ colsum_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ out,
             }
         }
         for (; r < M; r += stride) {
-            const uint4 u = ldg_v4(x + static_cast<long long>(r) * ld + ch * 8);
+            const uint4 u = ldg_v4(x + static_cast<long long>(M - 1 - r) * ld + ch * 8);
             const float2 x0 = unpack_bf16x2(u.x), x1 = unpack_bf16x2(u.y), x2 = unpack_bf16x2(u.z), x3 = unpack_bf16x2(u.w);
             a[0] += x0.x; a[1] += x0.y; a[2] += x1.x; a[3] += x1.y; a[4] += x2.x; a[5] += x2.y; a[6] += x3.x; a[7] += x3.y;
         }

@@ -13,7 +13,9 @@ int ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, 
            void* dx_drop, float* dgamma, float* dbeta, float* dbias, int rows, int H, float dropout_p,
            unsigned long long seed, unsigned stream_id, float in_dropout_p, unsigned in_stream_id, cudaStream_t st);
 int attn_fwd(const void* qkv, const float* mask_bias, void* ctx, float* lse, void* keep, int B, int S, int A, int H,
-             float dropout_p, unsigned long long seed, unsigned stream_id, cudaStream_t st);
+             float dropout_p, unsigned long long seed, unsigned stream_id, cudaStream_t st, bool mask_ready = false);
+int attn_mask_async(void* keep, int B, int S, int A, int H, float dropout_p, unsigned long long seed, unsigned stream_id,
+                    cudaEvent_t before_gemm, cudaStream_t main);
 int attn_bwd(const void* qkv, const float* mask_bias, const void* ctx, const float* lse, const void* keep,
              const void* dctx, void* dqkv, float* drow, int B, int S, int A, int H, float dropout_p,
              unsigned long long seed, unsigned stream_id, cudaStream_t st);
