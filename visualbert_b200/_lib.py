@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # VB_LIB_PATH: load another build of the same library (A/B timing of kernel variants on one GPU box, scripts/build_variant.sh)
 LIB_PATH = os.environ.get("VB_LIB_PATH") or os.path.join(_HERE, "lib", "libvbert_b200.so")
 
+ABI_VERSION = 2   # == VB_ABI_VERSION of include/vbert_b200.h (tests/test_abi.py keeps the two in step)
 VB_EPI_NONE, VB_EPI_GELU, VB_EPI_DGELU = 0, 1, 2
 
 c_void_p, c_int, c_i64, c_f32, c_u64, c_u32 = (
