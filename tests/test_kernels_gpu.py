@@ -126,7 +126,8 @@ def test_gemm_dropout_statistics_and_determinism():
 
 
 @pytest.mark.parametrize("env", [{"VB_GEMM_TMA_STORE": "0"}, {"VB_GEMM_TMA_STORE": "1"}, {"VB_GEMM_QUAD": "1"},
-                                 {"VB_GEMM_QUAD": "1", "VB_GEMM_TMA_STORE": "0"}, {"VB_GEMM_2CTA": "0"}])
+                                 {"VB_GEMM_QUAD": "1", "VB_GEMM_TMA_STORE": "0"}, {"VB_GEMM_QUAD": "2"}, {"VB_GEMM_GP_TILED": "0"},
+                                 {"VB_GEMM_2CTA": "0"}])
 def test_gemm_kernel_variants(env):
     """The GEMM picks its kernel per launch (CTA-pair / quad cluster with multicast B / single CTA; epilogue storing from
     registers or through staged TMA stores). Each family must pass the same checks: the variants are forced through the

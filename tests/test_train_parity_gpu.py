@@ -137,3 +137,15 @@ def test_layer_train_mode_matches_reference_math_with_the_same_masks(B, S, A, la
     for name, ref in pairs:
         r = relnorm(G[name], ref.grad)
         assert r < 2.5e-2, f"{name}: relative gradient error {r}"
+
+
+def test_side_stream_mask_generation_keeps_train_mode_parity():
+    """The opt-in dropout-mask generation on a side stream under the QKV GEMM (VB_MASK_OVERLAP=1) must give the same train-mode
+    parity (the GEMM variants are covered by test_kernels_gpu.py::test_gemm_kernel_variants): the switch is read once per
+    process, so the parity test reruns in a subprocess."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, VB_MASK_OVERLAP="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-k", "not side_stream"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
