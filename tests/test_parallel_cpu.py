@@ -105,3 +105,48 @@ def test_host_side_mlm_rows_equal_the_padded_label_scan():
         want = torch.nonzero(padded.reshape(-1) != -1).squeeze(1)
         assert torch.equal(BatchPrefetcher.labelled_rows(b), want)
     assert BatchPrefetcher.labelled_rows({"input_ids": torch.zeros(2, 3)}) is None
+
+
+def _seed_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from visualbert_b200 import BertConfig, TrainVisualBERTObjective, synthetic
+    torch.manual_seed(1234)
+    cfg = synthetic.bert_config_dict(1, 64, 1, 128, vocab=64)
+    m = TrainVisualBERTObjective(BertConfig.from_dict(cfg), "pretraining", visual_embedding_dim=16).bert
+    q.put((rank, m.dropout_state()["seed"], m.next_seed(), m.next_seed()))
+    dist.destroy_process_group()
+
+
+def test_dropout_seed_follows_manual_seed_differs_per_rank_and_round_trips():
+    """the encoder dropout used a constant seed — identical on every data-parallel rank, blind to
+    torch.manual_seed, and not resumable. Now: base seed from torch.initial_seed(), rank mixed in per forward,
+    dropout_state() / set_dropout_state() carry (seed, step)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_seed_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    (r0, base0, a0, b0), (r1, base1, a1, b1) = got
+    assert base0 == base1                      # same torch.manual_seed -> same base seed on both ranks
+    assert a0 != a1 and b0 != b1 and a0 != b0  # ... but different streams per rank and per step
+    sys.path.insert(0, ROOT)
+    from visualbert_b200 import BertConfig, TrainVisualBERTObjective, synthetic
+    cfg = synthetic.bert_config_dict(1, 64, 1, 128, vocab=64)
+    torch.manual_seed(1)
+    m1 = TrainVisualBERTObjective(BertConfig.from_dict(cfg), "pretraining", visual_embedding_dim=16).bert
+    torch.manual_seed(2)
+    m2 = TrainVisualBERTObjective(BertConfig.from_dict(cfg), "pretraining", visual_embedding_dim=16).bert
+    assert m1.dropout_state()["seed"] != m2.dropout_state()["seed"]
+    m1.next_seed(); m1.next_seed()
+    st = m1.dropout_state()
+    want = m1.next_seed()
+    m2.set_dropout_state(st)
+    assert m2.next_seed() == want and "dropout_seed" not in m1.state_dict()
