@@ -75,7 +75,14 @@ typedef struct {
      * 16 columns — so both touch whole 1 KB warp blocks instead of 32-byte pieces of 32 rows. vb_layer_fwd / _bwd use it
      * for vb_layer_acts.u whenever the shape allows. */
     int32_t gp_tiled;
+    /* delta_out != NULL (bf16 output, b_mn_major = 1, no bias / addend / dropout / epilogue; vb_gemm_delta_ok(M, N)): besides D
+     * the call writes delta_out[b][h][s] = sum_{d < 64} D[b * delta_seq + s][64 h + d] * delta_ctx[same element]
+     * (fp32 [M / delta_seq][N / 64][delta_seq]; delta_ctx bf16 [M, N] row-major) — the D = rowsum(dO * O) term of the attention
+     * backward, computed in the epilogue of the GEMM that produces dO (input gradient of attention.output.dense), where one
+     * thread holds two whole heads of a row. vb_layer_bwd uses it to drop the separate pass over dO and O. */
+    const void* delta_ctx; float* delta_out; int32_t delta_seq;
 } vb_gemm_args;
+int vb_gemm_delta_ok(int32_t M, int32_t N);
 /* 1 when gp_tiled is supported for this output shape on this build (M, N multiples of 256, CTA-pair kernels enabled) */
 int vb_gemm_gp_tiled_ok(int32_t M, int32_t N);
 

@@ -103,6 +103,30 @@ def test_gemm_dgrad_and_wgrad():
         assert _rel(dW, dY.float().t() @ X.float()) < 1e-4
 
 
+def test_gemm_dgrad_with_attention_delta_epilogue():
+    """vb_gemm_args.delta_out: the input-gradient GEMM that produces dO also writes D[b, h, s] = sum_d dO * O (the rowsum the attention
+    backward needs), from the bf16-rounded dO it stores — same numbers as a separate pass over dO and O."""
+    _lib, L, dev, st = _setup()
+    torch.manual_seed(5)
+    B, S, A = 4, 164, 12
+    M, N, K = B * S, A * 64, 768
+    if not L.vb_gemm_delta_ok(M, N):
+        pytest.skip("delta epilogue not available for this shape / build")
+    dY = torch.randn(M, K, device=dev).bfloat16(); W = (0.05 * torch.randn(K, N, device=dev)).bfloat16()
+    ctx = torch.randn(M, N, device=dev).bfloat16()
+    D = torch.zeros(M, N, device=dev, dtype=torch.bfloat16); D0 = torch.zeros_like(D)
+    delta = torch.full((B, A, S), float("nan"), device=dev)
+    base = dict(A=dY.data_ptr(), lda=K, B=W.data_ptr(), ldb=N, b_mn_major=1, M=M, N=N, K=K, ldd=N)
+    _gemm(_lib, L, st, D=D0.data_ptr(), **base)
+    _gemm(_lib, L, st, D=D.data_ptr(), delta_ctx=ctx.data_ptr(), delta_out=delta.data_ptr(), delta_seq=S, **base)
+    torch.cuda.synchronize()
+    assert torch.equal(D, D0)                                   # the stored gradient is unchanged
+    assert _rel(D, dY.float() @ W.float()) < BF16_TOL
+    ref = (D.float() * ctx.float()).view(B, S, A, 64).sum(-1).permute(0, 2, 1)
+    assert torch.isfinite(delta).all()
+    assert (delta - ref).abs().max().item() < 2e-3 * ref.abs().max().item() + 1e-3
+
+
 def test_gemm_dropout_statistics_and_determinism():
     _lib, L, dev, st = _setup()
     torch.manual_seed(3)

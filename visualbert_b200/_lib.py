@@ -31,6 +31,7 @@ class GemmArgs(ctypes.Structure):
         ("aux_in", c_void_p), ("aux_out", c_void_p), ("ld_aux", c_i64),
         ("dropout_p", c_f32), ("dropout_seed", c_u64), ("dropout_stream", c_u32),
         ("gp_tiled", c_int),
+        ("delta_ctx", c_void_p), ("delta_out", c_void_p), ("delta_seq", c_int),
     ]
 
 
@@ -73,7 +74,7 @@ VB_CAST_CHUNK = 8192
 
 # every symbol include/vbert_b200.h declares (checked by tests/test_abi.py without a GPU)
 EXPORTS = [
-    "vb_abi_version", "vb_last_error", "vb_launch_count", "vb_profile_enable", "vb_profile_read", "vb_gemm", "vb_gemm_gp_tiled_ok", "vb_layernorm_fwd", "vb_layernorm_bwd",
+    "vb_abi_version", "vb_last_error", "vb_launch_count", "vb_profile_enable", "vb_profile_read", "vb_gemm", "vb_gemm_gp_tiled_ok", "vb_gemm_delta_ok", "vb_layernorm_fwd", "vb_layernorm_bwd",
     "vb_attention_keep_bytes", "vb_attention_fwd", "vb_attention_bwd", "vb_mask_bias", "vb_cast_f32_to_bf16", "vb_cast_bf16_to_f32",
     "vb_colsum_bf16", "vb_cross_entropy_fwd", "vb_cross_entropy_bwd", "vb_layer_fwd", "vb_layer_bwd", "vb_embed_fwd", "vb_embed_bwd",
     "vb_bert_adam_step", "vb_cast_multi", "vb_encoder_arena_layout", "vb_encoder_fwd", "vb_encoder_bwd",

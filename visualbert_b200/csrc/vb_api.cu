@@ -131,10 +131,15 @@ int layer_bwd(const vb_layer_desc* d, const void* x_in, const vb_layer_acts* s, 
                   g->dln1_gamma, g->dln1_beta, g->db_attn_out, M, H, d->hidden_dropout, d->seed,
                   drop_stream(d->layer_index, kSiteAttnOut), 0.f, 0, st));
     VB_TRY(gemm(wgrad_args(dpm, s->ctx, g->dw_attn_out, M, H, H), st));
-    VB_TRY(gemm(dgrad_args(dpm, d->w_attn_out, w->d_ctx, M, H, H), st));
+    a = dgrad_args(dpm, d->w_attn_out, w->d_ctx, M, H, H);
+    // D = rowsum(dO * O) of the attention backward falls out of this GEMM's epilogue (a thread holds two whole heads of a row)
+    const bool fused_delta = gemm_delta_ok(M, H) && w->drow != nullptr &&
+                             attn_bwd_takes_delta(s->qkv, w->d_ctx, w->d_big, d->batch, d->seq, d->heads, H);
+    if (fused_delta) { a.delta_ctx = s->ctx; a.delta_out = w->drow; a.delta_seq = d->seq; }
+    VB_TRY(gemm(a, st));
     // ---- BertSelfAttention ----
     VB_TRY(attn_bwd(s->qkv, d->mask_bias, s->ctx, s->lse, s->keep_mask, w->d_ctx, w->d_big, w->drow, d->batch, d->seq, d->heads, H,
-                    d->attn_dropout, d->seed, drop_stream(d->layer_index, kSiteAttnProbs), st));
+                    d->attn_dropout, d->seed, drop_stream(d->layer_index, kSiteAttnProbs), st, fused_delta));
     VB_TRY(colsum(w->d_big, 3 * H, g->db_qkv, M, 3 * H, st));
     VB_TRY(gemm(wgrad_args(w->d_big, x_in, g->dw_qkv, M, 3 * H, H), st));
     a = dgrad_args(w->d_big, d->w_qkv, dx, M, 3 * H, H);

@@ -541,9 +541,27 @@ int attn_fwd(const void* qkv, const float* mask_bias, void* ctx, float* lse, voi
 
 static int g_bwd_minb = 3;
 
+static int bwd_impl() {   // VB_ATTN_BWD_IMPL = tc | head | staged
+    static int bimpl = -1;
+    if (bimpl < 0) {
+        const char* e = getenv("VB_ATTN_BWD_IMPL");
+        bimpl = e == nullptr ? 0 : (e[0] == 't' ? 0 : (e[0] == 's' ? 2 : 1));
+    }
+    return bimpl;
+}
+
+bool attn_bwd_takes_delta(const void* qkv, const void* dctx, void* dqkv, int B, int S, int A, int H) {
+    if (bwd_impl() != 0 || staged_only() || B <= 0 || S <= 0 || A <= 0 || H != A * kHd) return false;
+    AttnParams p;
+    memset(&p, 0, sizeof(p));
+    p.qkv = static_cast<const bf16*>(qkv); p.dctx = static_cast<const bf16*>(dctx); p.dqkv = static_cast<bf16*>(dqkv);
+    p.B = B; p.S = S; p.A = A; p.H = H;
+    return attn_bwd_tc_supported(p);
+}
+
 int attn_bwd(const void* qkv, const float* mask_bias, const void* ctx, const float* lse, const void* keep,
              const void* dctx, void* dqkv, float* drow, int B, int S, int A, int H, float dropout_p,
-             unsigned long long seed, unsigned stream_id, cudaStream_t st) {
+             unsigned long long seed, unsigned stream_id, cudaStream_t st, bool delta_ready) {
     AttnParams p;
     int rc = fill_params(p, qkv, mask_bias, const_cast<void*>(ctx), const_cast<float*>(lse), dctx, dqkv, drow,
                          const_cast<void*>(keep), B, S, A, H, dropout_p, seed, stream_id);
@@ -561,14 +579,12 @@ int attn_bwd(const void* qkv, const float* mask_bias, const void* ctx, const flo
     }
     dim3 grid((S + kBlk - 1) / kBlk, A, B);
     // VB_ATTN_BWD_IMPL = tc | head | staged: tcgen05 kernel by default (seq <= 192), then the whole-head mma.sync kernel
-    static int bimpl = -1;
-    if (bimpl < 0) {
-        const char* e = getenv("VB_ATTN_BWD_IMPL");
-        bimpl = e == nullptr ? 0 : (e[0] == 't' ? 0 : (e[0] == 's' ? 2 : 1));
-    }
+    const int bimpl = bwd_impl();
     if (bimpl == 0 && !staged_only() && attn_bwd_tc_supported(p)) {
-        rc = attn_delta(p, st);
-        if (rc) return rc;
+        if (!delta_ready) {   // D = rowsum(dO * O) — unless the GEMM that produced dO already wrote it (vb_gemm_args.delta_out)
+            rc = attn_delta(p, st);
+            if (rc) return rc;
+        }
         return attn_bwd_tc(p, st);
     }
     if (bimpl <= 1 && static_cast<int>(grid.x) <= kMaxSub && !staged_only()) return attn_bwd_head(p, static_cast<int>(grid.x), st);
@@ -603,6 +619,6 @@ int vb_attention_bwd(const void* qkv, const float* mask_bias, const void* ctx, c
                      const void* dctx, void* dqkv, float* drow, int32_t batch, int32_t seq, int32_t heads,
                      int32_t hidden, float dropout_p, uint64_t dropout_seed, uint32_t dropout_stream, void* stream) {
     return vb::attn_bwd(qkv, mask_bias, ctx, lse, keep_mask, dctx, dqkv, drow, batch, seq, heads, hidden, dropout_p,
-                        dropout_seed, dropout_stream, static_cast<cudaStream_t>(stream));
+                        dropout_seed, dropout_stream, static_cast<cudaStream_t>(stream), false);
 }
 }

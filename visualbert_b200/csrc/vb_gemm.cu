@@ -104,9 +104,12 @@ struct GemmParams {
     unsigned long long drop_seed;
     unsigned drop_stream;
     int m_fast;              // tile order of the CTA-pair kernel: m-blocks run faster than n-blocks (see decode_tile)
+    float* delta_out;        // EPI_DELTA: fp32 [rows / delta_seq][N / 64][delta_seq]
+    int delta_seq;
 };
 // vb_gemm_args.gp_tiled is honoured by the CTA-pair kernel with the staged-store epilogue on whole tiles only
 bool gemm_gp_tiled_ok(int M, int N);
+bool gemm_delta_ok(int M, int N);
 
 // UMMA shared-memory matrix descriptor (sm_100: version = 1), SWIZZLE_128B.
 //  K-major  operand tile [rows][64]: 8-row groups are 1024 B apart (SBO); LBO unused.
@@ -181,8 +184,12 @@ __device__ __forceinline__ void store16_bf16(bf16* p, const float (&f)[16]) {
 // _T: gelu'(u) is kept in the TILE-NATIVE layout (vb_gemm_args.gp_tiled): the only reader of that tensor is the epilogue of the
 // backward GEMM with the same tiling, where the same thread holds the same 16 columns — so it is written and read as whole
 // 1 KB warp blocks (lane l: 32 bytes at block + 32 l) instead of 32-byte pieces of 32 different rows.
+// EPI_DELTA: plain bf16 store plus the attention backward's D[b, head, s] = sum_d dO[row, head, d] * O[row, head, d] (vb_gemm_args.delta_*):
+// the GEMM that PRODUCES dO (input gradient of attention.output.dense) has, in each epilogue thread, 128 consecutive columns of one row —
+// two whole heads — so the row-wise dot product with O needs no exchange; O is read like a residual operand (whole tile row requested
+// before the accumulator barrier).
 enum { EPI_GENERIC = 0, EPI_BIAS = 1, EPI_RESID = 2, EPI_DROP_RESID = 3, EPI_GELU_FWD = 4, EPI_DGELU_BWD = 5, EPI_GELU_FWD_T = 6,
-       EPI_DGELU_BWD_T = 7 };
+       EPI_DGELU_BWD_T = 7, EPI_DELTA = 8 };
 __host__ __device__ constexpr bool epi_is_gelu(int e) { return e == EPI_GELU_FWD || e == EPI_GELU_FWD_T; }
 __host__ __device__ constexpr bool epi_is_dgelu(int e) { return e == EPI_DGELU_BWD || e == EPI_DGELU_BWD_T; }
 
@@ -214,7 +221,7 @@ __device__ __forceinline__ void epilogue16(const GemmParams& p, int row, int col
                 for (int i = 0; i < 8; ++i) x[8 * h + i] = ((keep >> i) & 1u) ? x[8 * h + i] * p.drop_scale : 0.0f;
             }
         }
-        if (EPI == EPI_RESID || EPI == EPI_DROP_RESID || (kGeneric && p.addend != nullptr)) {
+        if (EPI == EPI_RESID || EPI == EPI_DROP_RESID || (kGeneric && p.addend != nullptr)) {   // (EPI_DELTA reads ex in the caller)
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float2 t = unpack_bf16x2(ex[i]);
@@ -569,7 +576,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
     // Epilogues that read a second operand (residual / gelu') hold the whole tile row of it in registers (see below): the
     // four control warps hand registers to the eight epilogue warps (128 * 72 + 256 * 216 = 384 * 168).
-    constexpr bool kDeepEx = VB_GEMM_DEEP_EX && !OUT_F32 && (EPI == EPI_RESID || EPI == EPI_DROP_RESID || epi_is_dgelu(EPI));
+    constexpr bool kDeepEx = VB_GEMM_DEEP_EX && !OUT_F32 && (EPI == EPI_RESID || EPI == EPI_DROP_RESID || EPI == EPI_DELTA || epi_is_dgelu(EPI));
     if (warp == 0) {
         if constexpr (kDeepEx) reg_dec<72>();
         {
@@ -696,7 +703,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             constexpr int kExAhead = 4;
             const bf16* exp_ = nullptr;
             if constexpr (!OUT_F32) {
-                constexpr bool kWantAdd = EPI == EPI_RESID || EPI == EPI_DROP_RESID;
+                constexpr bool kWantAdd = EPI == EPI_RESID || EPI == EPI_DROP_RESID || EPI == EPI_DELTA;   // EPI_DELTA: addend = O
                 if (kWantAdd || (EPI == EPI_GENERIC && p.addend != nullptr)) exp_ = p.addend + static_cast<long long>(row) * p.ld_add;
                 else if (EPI == EPI_DGELU_BWD || (EPI == EPI_GENERIC && p.epilogue == VB_EPI_DGELU)) exp_ = p.aux_in + static_cast<long long>(row) * p.ld_aux;
                 if (row >= p.M) exp_ = nullptr;
@@ -725,6 +732,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 mbar_wait(tfull_bar(acc), acc_phase);
                 tcgen05_fence_after();
                 tmem_ld_32x32b_x16(taddr0, v[0]);
+                [[maybe_unused]] float hsum = 0.f;
 #pragma unroll 1
                 for (int k0 = 0; k0 < NCH; k0 += kExAhead) {
 #pragma unroll
@@ -743,6 +751,13 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                             if constexpr (kTmaSt) {
                                 uint32_t o0[8];
                                 epilogue16<OUT_F32, EPI, true>(p, row, col, has_bias ? sb + half * (BLOCK_N / 2) + k * 16 : nullptr, e, x, o0);
+                                if constexpr (EPI == EPI_DELTA) {   // dot product of the ROUNDED dO (what the attention kernel will read) with O
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) {
+                                        const float2 a = unpack_bf16x2(o0[i]), b = unpack_bf16x2(e[i]);
+                                        hsum = fmaf(a.x, b.x, fmaf(a.y, b.y, hsum));
+                                    }
+                                }
                                 if (kk == 0) slab_free();
                                 stage16(kk, o0);
                             } else {
@@ -751,6 +766,14 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                         }
                     }
                     if constexpr (kTmaSt) flush(&tmD, col0 + k0 * 16);
+                    if constexpr (EPI == EPI_DELTA) {   // the group's four chunks are exactly one head (col0 is a multiple of 128)
+                        const int head = (col0 + k0 * 16) >> 6;
+                        if (row < p.M && col0 + k0 * 16 < p.N) {
+                            const int bi = row / p.delta_seq, si = row - bi * p.delta_seq;
+                            p.delta_out[(static_cast<long long>(bi) * (p.N >> 6) + head) * p.delta_seq + si] = hsum;
+                        }
+                        hsum = 0.f;
+                    }
                 }
             } else {
                 // Residual / gelu' operand of this thread's row (generic kernel): one 32-byte load per 16-column chunk,
@@ -1032,6 +1055,11 @@ static bool use_2cta() {
     if (v < 0) { const char* e = getenv("VB_GEMM_2CTA"); v = (e != nullptr && atoi(e) == 0) ? 0 : 1; }
     return v == 1;
 }
+bool gemm_delta_ok(int M, int N) {
+    static const int off = [] { const char* e = getenv("VB_GEMM_DELTA"); return (e != nullptr && atoi(e) == 0) ? 1 : 0; }();
+    const int n_pad256 = (N + 255) / 256 * 256;
+    return !off && use_2cta() && M >= 256 && N >= 256 && N % 64 == 0 && (n_pad256 - N) * 8 <= N;
+}
 bool gemm_gp_tiled_ok(int M, int N) {
     static const int off = [] { const char* e = getenv("VB_GEMM_GP_TILED"); return (e != nullptr && atoi(e) == 0) ? 1 : 0; }();
     return !off && use_2cta() && M >= 256 && M % 256 == 0 && N % 256 == 0;
@@ -1053,6 +1081,10 @@ int gemm(const vb_gemm_args& a, cudaStream_t st) {
     VB_REQUIRE(!a.d_fp32 || (a.epilogue == VB_EPI_NONE && !a.addend && a.dropout_p == 0.0f),
                "vb_gemm: fp32-accumulate output supports bias only");
     VB_REQUIRE(a.dropout_p >= 0.0f && a.dropout_p < 1.0f, "vb_gemm: dropout_p out of range");
+    VB_REQUIRE(!a.delta_out || (gemm_delta_ok(a.M, a.N) && a.delta_ctx && a.delta_seq > 0 && a.M % a.delta_seq == 0 && !a.d_fp32 &&
+                                !a.a_mn_major && a.b_mn_major && !a.bias && !a.addend && a.dropout_p == 0.0f && a.epilogue == VB_EPI_NONE &&
+                                (reinterpret_cast<uintptr_t>(a.delta_ctx) & 31) == 0),
+               "vb_gemm: delta_out needs a plain bf16 input-gradient GEMM (b_mn_major, no bias / addend / dropout) and vb_gemm_delta_ok(M, N)");
     VB_REQUIRE(!a.gp_tiled || (gemm_gp_tiled_ok(a.M, a.N) && !a.d_fp32 && !a.a_mn_major && (a.epilogue == VB_EPI_GELU || a.epilogue == VB_EPI_DGELU)),
                "vb_gemm: gp_tiled needs a GELU / DGELU epilogue and vb_gemm_gp_tiled_ok(M, N)");
 
@@ -1070,6 +1102,10 @@ int gemm(const vb_gemm_args& a, cudaStream_t st) {
     p.aux_in = static_cast<const bf16*>(a.aux_in);
     p.aux_out = static_cast<bf16*>(a.aux_out);
     p.ld_aux = a.ld_aux;
+    if (a.delta_out) {   // O rides the residual-operand path of the epilogue (read, not added)
+        p.addend = static_cast<const bf16*>(a.delta_ctx); p.ld_add = a.N;
+        p.delta_out = a.delta_out; p.delta_seq = a.delta_seq;
+    }
     {
         static const int order_off = [] { const char* e = getenv("VB_GEMM_TILE_ORDER"); return (e != nullptr && atoi(e) == 0) ? 1 : 0; }();
         p.m_fast = (!order_off && (a.M + 255) / 256 < (a.N + 255) / 256) ? 1 : 0;
@@ -1104,6 +1140,7 @@ int gemm(const vb_gemm_args& a, cudaStream_t st) {
             if (a.epilogue == VB_EPI_GELU && !drop && !add) epi = a.gp_tiled ? EPI_GELU_FWD_T : EPI_GELU_FWD;
             else if (a.epilogue == VB_EPI_DGELU && !drop && !add) epi = a.gp_tiled ? EPI_DGELU_BWD_T : EPI_DGELU_BWD;
             else if (a.epilogue == VB_EPI_NONE) epi = add ? (drop ? EPI_DROP_RESID : EPI_RESID) : (drop ? EPI_GENERIC : EPI_BIAS);
+            if (a.delta_out) epi = EPI_DELTA;
             VB_REQUIRE(!a.gp_tiled || epi == EPI_GELU_FWD_T || epi == EPI_DGELU_BWD_T,
                        "vb_gemm: gp_tiled needs a plain GELU / DGELU epilogue (no dropout, no addend)");
             // Staged TMA stores where the epilogue, not the main loop, bounds the tile (measured r02, same box, us per
@@ -1111,7 +1148,7 @@ int gemm(const vb_gemm_args& a, cudaStream_t st) {
             // 3-4 us SLOWER — the slabs cost a pipeline stage). VB_GEMM_TMA_STORE=0 / 1 forces never / wherever possible.
             static const int tma_mode = [] { const char* e = getenv("VB_GEMM_TMA_STORE"); return e ? atoi(e) : 2; }();
             bool tma_st = false;
-            if (tma_mode == 1 || epi == EPI_GELU_FWD_T) tma_st = epi != EPI_GENERIC;
+            if (tma_mode == 1 || epi == EPI_GELU_FWD_T || epi == EPI_DELTA) tma_st = epi != EPI_GENERIC;
             else if (tma_mode != 0)
                 tma_st = epi_is_gelu(epi) || epi_is_dgelu(epi) || ((epi == EPI_RESID || epi == EPI_DROP_RESID) && a.K <= 1536);
             // output tensor maps for the staged TMA stores: 64-column x 32-row boxes (one epilogue warp's slab)
@@ -1175,6 +1212,7 @@ int gemm(const vb_gemm_args& a, cudaStream_t st) {
                     case EPI_BIAS: return (tma_st ? launch2<false, true, false, EPI_BIAS, true>(ta, tb, td, tx, p, st) : launch2<false, true, false, EPI_BIAS, false>(ta, tb, td, tx, p, st));
                     case EPI_RESID: return (tma_st ? launch2<false, true, false, EPI_RESID, true>(ta, tb, td, tx, p, st) : launch2<false, true, false, EPI_RESID, false>(ta, tb, td, tx, p, st));
                     case EPI_DGELU_BWD: return (tma_st ? launch2<false, true, false, EPI_DGELU_BWD, true>(ta, tb, td, tx, p, st) : launch2<false, true, false, EPI_DGELU_BWD, false>(ta, tb, td, tx, p, st));
+                    case EPI_DELTA: return launch2<false, true, false, EPI_DELTA, true>(ta, tb, td, tx, p, st);
                     case EPI_DGELU_BWD_T: return (tma_st ? launch2<false, true, false, EPI_DGELU_BWD_T, true>(ta, tb, td, tx, p, st) : launch2<false, true, false, EPI_DGELU_BWD_T, false>(ta, tb, td, tx, p, st));
                     default: return launch2<false, true, false>(ta, tb, ta, ta, p, st);
                 }
@@ -1234,6 +1272,7 @@ int vb_profile_read(double* ms, double* work, int64_t* launches) {
     vb::g_prof.clear();
     return 0;
 }
+int vb_gemm_delta_ok(int32_t M, int32_t N) { return vb::gemm_delta_ok(M, N) ? 1 : 0; }
 int vb_gemm_gp_tiled_ok(int32_t M, int32_t N) { return vb::gemm_gp_tiled_ok(M, N) ? 1 : 0; }
 int vb_gemm(const vb_gemm_args* args, void* stream) {
     if (!args) { vb::set_error("vb_gemm: null args"); return 2; }

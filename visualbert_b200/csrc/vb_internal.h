@@ -7,6 +7,7 @@ namespace vb {
 
 int gemm(const vb_gemm_args& a, cudaStream_t st);
 bool gemm_gp_tiled_ok(int M, int N);
+bool gemm_delta_ok(int M, int N);
 int ln_fwd(const void* x, long long ldx, const float* gamma, const float* beta, void* y, long long ldy, float* mean,
            float* rstd, int rows, int H, float eps, cudaStream_t st);
 int ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
@@ -18,7 +19,9 @@ int attn_mask_async(void* keep, int B, int S, int A, int H, float dropout_p, uns
                     cudaEvent_t before_gemm, cudaStream_t main);
 int attn_bwd(const void* qkv, const float* mask_bias, const void* ctx, const float* lse, const void* keep,
              const void* dctx, void* dqkv, float* drow, int B, int S, int A, int H, float dropout_p,
-             unsigned long long seed, unsigned stream_id, cudaStream_t st);
+             unsigned long long seed, unsigned stream_id, cudaStream_t st, bool delta_ready = false);
+// true when attn_bwd for this shape runs the kernel that takes D = rowsum(dO * O) from `drow` (so a caller may provide it)
+bool attn_bwd_takes_delta(const void* qkv, const void* dctx, void* dqkv, int B, int S, int A, int H);
 long long attn_keep_bytes(int B, int S, int A);
 int colsum(const void* x, long long ld, float* out, int M, int N, cudaStream_t st);
 int cast_f32_bf16(const float* src, void* dst, long long n, cudaStream_t st);
