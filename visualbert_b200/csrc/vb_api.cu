@@ -1,5 +1,5 @@
 // vb_api.cu — layer-level entry points of the C ABI: one call launches every kernel of a BertLayer
-// forward (7 launches) or backward (14 launches), or of the visual+text embedding block.
+// forward (8 launches with attention dropout) or backward (13 launches), or of the visual+text embedding block.
 //
 // Kernel sequence of vb_layer_fwd (reference modeling.py:331-341):
 //   1 GEMM   qkv  = x Wqkv^T + b                       (M.py:232-234, three Linears fused into N = 3H)
