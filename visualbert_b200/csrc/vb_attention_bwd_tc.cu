@@ -43,15 +43,6 @@ __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap
         ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
-__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
-    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
-    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
-    d |= 1ull << 46;
-    d |= 2ull << 61;
-    return d;
-}
 __device__ __forceinline__ uint32_t idesc_bw(int m, int n, bool a_mn, bool b_mn) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn) << 15) | (static_cast<uint32_t>(b_mn) << 16) |
            (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
@@ -120,7 +111,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const BwLayout L = bw_layout(bp.npq, bp.r2pad, bp.nstage);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.S, npq = bp.npq, nkt = bp.nkt, nstage = bp.nstage;
-    const int natoms = (npq + 63) / 64;
 
     auto q_tile = [&](int s) { return base + s * L.stage_bytes; };
     auto do_tile = [&](int s) { return base + s * L.stage_bytes + L.qbytes; };
