@@ -118,3 +118,21 @@ def test_lazy_output_dict_defers_and_caches():
     assert dict(e.items()) == {"x": 7} and e.get("y", 3) == 3
     e["x"] = 8
     assert e["x"] == 8
+
+
+def test_documented_tile_native_layout_is_a_permutation():
+    """include/vbert_b200.h documents where vb_gemm_args.gp_tiled puts element (row, col) of gelu'(u); the formula must be a bijection
+    onto [0, M * N) in 16-element groups (tests/test_kernels_gpu.py checks the kernels against the same formula on the GPU)."""
+    M, N = 512, 768
+    row = torch.arange(M).view(M, 1).expand(M, N)
+    col = torch.arange(N).view(1, N).expand(M, N)
+    mb, r, q, l = row // 256, (row % 256) // 128, (row % 128) // 32, row % 32
+    nb, half, k, e = col // 256, (col % 256) // 128, (col % 128) // 16, col % 16
+    w = 4 * half + q
+    off = ((((mb * (N // 256) + nb) * 2 + r) * 8 + w) * 8 + k) * 512 + 16 * l + e
+    assert off.min() == 0 and off.max() == M * N - 1 and torch.unique(off).numel() == M * N
+    # the same thing as a view / permute of the flat buffer (what the GPU test uses)
+    flat = torch.empty(M * N, dtype=torch.int64)
+    flat[off.reshape(-1)] = (row * N + col).reshape(-1)
+    t = flat.view(M // 256, N // 256, 2, 2, 4, 8, 32, 16).permute(0, 2, 4, 6, 1, 3, 5, 7).reshape(M, N)
+    assert torch.equal(t, row * N + col)
